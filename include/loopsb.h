@@ -1,0 +1,204 @@
+/* include/loopsb.h -- the C ABI of loops-b200 (libloopsb200.so).
+ *
+ * gunrock/loops is a header-only C++/CUDA template library: it has no FFI of
+ * its own. The "drop-in boundary" is therefore the set of host entry points in
+ * reference include/loops/algorithms/spmv/ (each takes an owning container, x, y
+ * and a stream) plus the schedule/layout template API those kernels are written
+ * against. This header is what those host entry points bind to in loops-b200:
+ * plain pointers and sizes, no C++ or torch types, one shared object of
+ * hand-written sm_100a kernels behind it. The C++ mirror of the reference API
+ * that calls these functions lives in include/loops/ (same namespaces and
+ * names); the Python/ctypes binding used by tests/ and bench.py lives in
+ * loops_b200/. INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless the name says `host`.
+ *  - ids are int32 (the reference instantiates index_t = offset_t = int
+ *    everywhere: examples/spmv/merge_path.cu:18-20); tiles+atoms < 2^31
+ *    (reference util/search.hxx:46-47 has the same cap).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *    Calls are asynchronous on that stream unless stated otherwise.
+ *  - Every function returns a loopsb_status_t; nothing throws across the
+ *    boundary. loopsb_last_error() gives the CUDA / argument detail.
+ *  - y is always fully OVERWRITTEN (rows with no atoms get 0); the reference's
+ *    "y must be pre-zeroed" precondition for its atomic kernels
+ *    (algorithms/spmv/coo_thread_mapped.cuh:14-15, ell_merge_path.cuh:113-114)
+ *    is tolerated but not required.
+ *  - There is no CPU fallback: without a CUDA device every compute entry point
+ *    returns LOOPSB_ERR_CUDA.
+ */
+#ifndef LOOPSB_H_
+#define LOOPSB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LOOPSB_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  LOOPSB_OK = 0,
+  LOOPSB_ERR_INVALID = 1,     /* bad argument (null pointer, negative size ...) */
+  LOOPSB_ERR_CUDA = 2,        /* CUDA runtime error, see loopsb_last_error()   */
+  LOOPSB_ERR_UNSUPPORTED = 3, /* (schedule, layout, dtype) has no kernel       */
+  LOOPSB_ERR_ALLOC = 4
+} loopsb_status_t;
+
+/* Same order as reference schedule::algorithms_t (schedule.hxx:26-32). */
+typedef enum {
+  LOOPSB_SCHED_MERGE_PATH_FLAT = 0,
+  LOOPSB_SCHED_WORK_ORIENTED = 1,
+  LOOPSB_SCHED_THREAD_MAPPED = 2,
+  LOOPSB_SCHED_GROUP_MAPPED = 3
+} loopsb_schedule_t;
+
+/* Which in-tree layout view a descriptor stands for (container/layout.hxx). */
+typedef enum {
+  LOOPSB_LAYOUT_CSR = 0,  /* offsets[T+1]                     layout.hxx:87-149  */
+  LOOPSB_LAYOUT_COO = 1,  /* tiles == atoms == nnz            layout.hxx:385-421 */
+  LOOPSB_LAYOUT_ELL = 2,  /* pitch atoms per tile             layout.hxx:443-496 */
+  LOOPSB_LAYOUT_BCSR = 3, /* offsets over block-rows          layout.hxx:239-285 */
+  LOOPSB_LAYOUT_CSC = 4,  /* offsets over columns             layout.hxx:312-359 */
+  LOOPSB_LAYOUT_DIA = 5,  /* pitch = number of diagonals      layout.hxx:166-217 */
+  LOOPSB_LAYOUT_FLAT = 6  /* windows of `pitch` (=K) atoms    partitioning.hxx:71-141 */
+} loopsb_layout_kind_t;
+
+/* POD image of a layout view: enough to answer the six contract questions
+ * (num_tiles, num_atoms, tile_begin, tile_end, tile_size, tile_end_iter). */
+typedef struct loopsb_layout {
+  int32_t kind;           /* loopsb_layout_kind_t                              */
+  int32_t num_tiles;
+  int32_t num_atoms;
+  int32_t pitch;          /* ELL/DIA: atoms per tile; FLAT: K; else unused     */
+  const int32_t* offsets; /* CSR/CSC/BCSR: device array [num_tiles+1]; else 0  */
+} loopsb_layout_t;
+
+/* ---------------------------------------------------------------------------
+ * Library / device
+ * ------------------------------------------------------------------------- */
+int loopsb_version(void);
+const char* loopsb_status_string(int status);
+const char* loopsb_last_error(void);
+/* SM count and max resident threads of the current device. */
+int loopsb_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ---------------------------------------------------------------------------
+ * Plan: what the reference calls schedule::merge_path::preprocess_t
+ * (schedule/merge_path_flat.hxx:92-172) generalised to every schedule -- the
+ * per-matrix, data-independent-of-values set-up: merge-path tile coordinates,
+ * work-oriented per-block coordinates, carry-out workspace, launch geometry.
+ * Borrowing rule: `lay->offsets` must stay valid while the plan is used.
+ * ------------------------------------------------------------------------- */
+typedef struct loopsb_plan loopsb_plan_t;
+
+typedef struct loopsb_plan_info {
+  int32_t schedule;
+  int32_t layout_kind;
+  int32_t threads_per_block;   /* reference-visible schedule geometry          */
+  int32_t items_per_thread;
+  int64_t num_merge_tiles;     /* merge_path_flat: ceil((T+A)/(TPB*IPT))       */
+  int32_t grid_blocks;         /* CTAs the SpMV kernel launches                */
+  int32_t cta_threads;         /* threads per CTA of the SpMV kernel           */
+  int32_t launches_per_spmv;   /* kernels enqueued by one loopsb_spmv_f32 call */
+  int32_t smem_bytes;          /* dynamic shared memory per CTA                */
+  int64_t workspace_bytes;     /* device memory owned by the plan              */
+} loopsb_plan_info_t;
+
+int loopsb_plan_create(loopsb_plan_t** out, const loopsb_layout_t* lay,
+                       int schedule, void* stream);
+int loopsb_plan_destroy(loopsb_plan_t* plan);
+int loopsb_plan_info(const loopsb_plan_t* plan, loopsb_plan_info_t* info);
+/* Copy the merge-path tile start coordinates S(b * TPB*IPT), b = 0..M, to a
+ * HOST array of 2*(M+1) int32 (x0,y0,x1,y1,...). Synchronises. This is what
+ * the reference's generate_search_coordinates (merge_path_flat.hxx:45-76)
+ * materialises; exposed for parity tests. */
+int loopsb_plan_merge_coords_host(const loopsb_plan_t* plan, int32_t* host_xy,
+                                  int64_t capacity_pairs);
+
+/* ---------------------------------------------------------------------------
+ * SpMV  y = A * x, fp32 values, int32 ids. Replaces the host entry points
+ *   algorithms::spmv::merge_path_flat   merge_path_flat.cuh:96-139
+ *   algorithms::spmv::work_oriented     work_oriented.cuh:102-120
+ *   algorithms::spmv::thread_mapped     thread_mapped.cuh:69-91
+ *   algorithms::spmv::group_mapped      group_mapped.cuh:72-104
+ *   algorithms::spmv::coo_thread_mapped coo_thread_mapped.cuh:61-89
+ *   algorithms::spmv::ell_thread_mapped ell_thread_mapped.cuh:52-76
+ *   algorithms::spmv::ell_merge_path    ell_merge_path.cuh:76-126
+ * selected by (plan schedule, plan layout kind). `row_indices` is read only
+ * for COO. For ELL, `col_indices`/`values` are the row-major rows*pitch slabs
+ * with column -1 in padding slots (container/ell.hxx:31-36).
+ * ------------------------------------------------------------------------- */
+int loopsb_spmv_f32(loopsb_plan_t* plan, const float* values,
+                    const int32_t* col_indices, const int32_t* row_indices,
+                    const float* x, float* y, int32_t num_rows,
+                    int32_t num_cols, void* stream);
+
+/* BCSR R x C dense blocks (values[b*R*C + i*C + j], container/bcsr.hxx:14-22),
+ * one thread per block-row, fp32 FMA. Replaces
+ * algorithms::spmv::bcsr_thread_mapped (bcsr_thread_mapped.cuh:88-123).
+ * R == C in {2,3,4}. x must be padded to num_block_cols*C. */
+int loopsb_spmv_bcsr_f32(int32_t R, int32_t C, const loopsb_layout_t* lay,
+                         const float* values, const int32_t* block_col_indices,
+                         const float* x_padded, float* y, int32_t num_rows,
+                         void* stream);
+
+/* BCSR 4x4, bf16 values and x, fp32 accumulate and y, on the tcgen05 tensor
+ * cores (BASELINE.json config 4). The plan must have been created from a
+ * LOOPSB_LAYOUT_BCSR descriptor with LOOPSB_SCHED_THREAD_MAPPED. */
+int loopsb_spmv_bcsr4x4_bf16(loopsb_plan_t* plan, const uint16_t* values_bf16,
+                             const int32_t* block_col_indices,
+                             const uint16_t* x_bf16_padded, float* y,
+                             int32_t num_rows, void* stream);
+
+/* Host-buffer convenience with the flow of the reference's example mains
+ * (examples/spmv/merge_path.cu:17-50): upload CSR + x, run, download y,
+ * synchronise. *kernel_ms (optional) receives the CUDA-event time of the SpMV
+ * launches only (what the reference's util::timer_t reports). */
+int loopsb_spmv_csr_host_f32(int schedule, int32_t num_rows, int32_t num_cols,
+                             int32_t nnz, const int32_t* host_offsets,
+                             const int32_t* host_indices,
+                             const float* host_values, const float* host_x,
+                             float* host_y, float* kernel_ms);
+
+/* ---------------------------------------------------------------------------
+ * Schedule index-stream emission (parity instrument; not on the SpMV path).
+ * Runs the loops-b200 schedule::setup<> iterators (include/loops/schedule/)
+ * with a recording body and writes, for every atom a:
+ *   visitor[a] = global thread id that was handed the atom
+ *   step[a]    = ordinal of that hand-out within the thread's own sequence
+ *   tile[a]    = tile id handed out with it
+ *   visits[a] += 1
+ * (caller pre-fills visitor/step/tile with -1 and visits with 0).
+ *   work_oriented : extra_a = commit[A] (0 first complete tile -> atomic-if-
+ *                   nonzero, 1 later complete tile -> store, 2 remainder),
+ *                   extra_b = map[grid*TPB*4] = {st.x, st.y, en.x, en.y}
+ *   merge_path_flat: dense_{tile,atom,emit}[M*TPB*IPT] per (block,thread,item)
+ *                   exactly as the reference kernel sees them
+ *                   (algorithms/spmv/merge_path_flat.cuh:71-82),
+ *                   extra_b = thread_start[M*TPB*2]
+ * grid_blocks is only read for thread_mapped and work_oriented (the other two
+ * derive their grid from the layout like the reference wrappers do).
+ * (TPB, IPT) for merge_path_flat: (128,8) = reference sm_100 f32 tuning
+ * (algorithms/spmv/launch_box.hxx:66-68), (128,7) fallback, (128,5) ELL.
+ * Synchronises before returning.
+ * ------------------------------------------------------------------------- */
+int loopsb_emit_schedule(const loopsb_layout_t* lay, int schedule,
+                         int32_t grid_blocks, int32_t threads_per_block,
+                         int32_t items_per_thread, int32_t* visitor,
+                         int32_t* step, int32_t* tile, int32_t* visits,
+                         int32_t* extra_a, int32_t* extra_b,
+                         int32_t* dense_tile, int32_t* dense_atom,
+                         int32_t* dense_emit, int64_t dense_len, void* stream);
+
+/* Grid the reference-compatible work_oriented launch uses on this device:
+ * resident blocks per SM (occupancy API) x SM count, 128 threads per block
+ * (algorithms/spmv/work_oriented.cuh:112-113). */
+int loopsb_work_oriented_grid(int32_t* grid_blocks);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+
+#endif /* LOOPSB_H_ */

@@ -1,0 +1,125 @@
+"""ctypes binding of the C ABI in include/loopsb.h (libloopsb200.so).
+
+The shared object is built in-tree by ``__graft_entry__.build()`` /
+``make -C loops_b200/csrc``. There is no fallback of any kind: if the library
+is missing, ``load()`` raises, and every compute entry point returns an error
+status when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libloopsb200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_ALLOC = range(5)
+
+# reference schedule::algorithms_t order (schedule.hxx:26-32)
+SCHED_MERGE_PATH_FLAT, SCHED_WORK_ORIENTED, SCHED_THREAD_MAPPED, SCHED_GROUP_MAPPED = range(4)
+SCHEDULE_NAMES = {
+    "merge_path_flat": SCHED_MERGE_PATH_FLAT,
+    "work_oriented": SCHED_WORK_ORIENTED,
+    "thread_mapped": SCHED_THREAD_MAPPED,
+    "group_mapped": SCHED_GROUP_MAPPED,
+}
+(LAYOUT_CSR, LAYOUT_COO, LAYOUT_ELL, LAYOUT_BCSR, LAYOUT_CSC, LAYOUT_DIA,
+ LAYOUT_FLAT) = range(7)
+
+
+class LoopsbError(RuntimeError):
+    def __init__(self, status: int, where: str, detail: str):
+        self.status = status
+        super().__init__(f"{where}: status {status} ({detail})")
+
+
+class LayoutDesc(C.Structure):
+    """loopsb_layout_t"""
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("num_tiles", C.c_int32),
+        ("num_atoms", C.c_int32),
+        ("pitch", C.c_int32),
+        ("offsets", C.c_void_p),
+    ]
+
+
+class PlanInfo(C.Structure):
+    """loopsb_plan_info_t"""
+    _fields_ = [
+        ("schedule", C.c_int32),
+        ("layout_kind", C.c_int32),
+        ("threads_per_block", C.c_int32),
+        ("items_per_thread", C.c_int32),
+        ("num_merge_tiles", C.c_int64),
+        ("grid_blocks", C.c_int32),
+        ("cta_threads", C.c_int32),
+        ("launches_per_spmv", C.c_int32),
+        ("smem_bytes", C.c_int32),
+        ("workspace_bytes", C.c_int64),
+    ]
+
+
+# every symbol include/loopsb.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SIGNATURES = {
+    "loopsb_version": (C.c_int, []),
+    "loopsb_status_string": (C.c_char_p, [C.c_int]),
+    "loopsb_last_error": (C.c_char_p, []),
+    "loopsb_device_info": (C.c_int, [C.POINTER(C.c_int32)] * 3),
+    "loopsb_plan_create": (C.c_int, [C.POINTER(_P), C.POINTER(LayoutDesc), C.c_int, _P]),
+    "loopsb_plan_destroy": (C.c_int, [_P]),
+    "loopsb_plan_info": (C.c_int, [_P, C.POINTER(PlanInfo)]),
+    "loopsb_plan_merge_coords_host": (C.c_int, [_P, _P, C.c_int64]),
+    "loopsb_spmv_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "loopsb_spmv_bcsr_f32": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(LayoutDesc), _P, _P, _P, _P, C.c_int32, _P]),
+    "loopsb_spmv_bcsr4x4_bf16": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P]),
+    "loopsb_spmv_csr_host_f32": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.POINTER(C.c_float)]),
+    "loopsb_emit_schedule": (C.c_int, [C.POINTER(LayoutDesc), C.c_int, C.c_int32, C.c_int32, C.c_int32,
+                                       _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _P]),
+    "loopsb_work_oriented_grid": (C.c_int, [C.POINTER(C.c_int32)]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libloopsb200.so (once). Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C loops_b200/csrc`. loops-b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, where: str) -> None:
+    if status != OK:
+        lib = load()
+        detail = lib.loopsb_last_error().decode(errors="replace")
+        raise LoopsbError(status, where, detail or lib.loopsb_status_string(status).decode())
+
+
+def ptr(t) -> int | None:
+    """Device/host address of a torch tensor or numpy array (None -> NULL)."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return t.data_ptr() if t.numel() else None
+    return t.ctypes.data if t.size else None
+
+
+def stream_ptr(stream=None):
+    """cudaStream_t of a torch stream (default: torch's current stream)."""
+    import torch
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    return C.c_void_p(stream.cuda_stream)

@@ -1,0 +1,151 @@
+"""``loops::algorithms::spmv::*`` host entry points (reference
+include/loops/algorithms/spmv/*.cuh), same names and argument meaning:
+
+    merge_path_flat(csr, x, y, stream)   -> timer_t   merge_path_flat.cuh:96-139
+    work_oriented(csr, x, y, stream)     -> None      work_oriented.cuh:102-120
+    thread_mapped(csr, x, y, stream)     -> None      thread_mapped.cuh:69-91
+    group_mapped(csr, x, y, stream)      -> None      group_mapped.cuh:72-104
+    coo_thread_mapped(coo, x, y, stream) -> timer_t   coo_thread_mapped.cuh:61-89
+    ell_thread_mapped(ell, x, y, stream) -> None      ell_thread_mapped.cuh:52-76
+    ell_merge_path(ell, x, y, stream)    -> timer_t   ell_merge_path.cuh:76-126
+    bcsr_thread_mapped(bcsr, x, y, stream) -> timer_t bcsr_thread_mapped.cuh:88-123
+
+Each call goes straight through the C ABI (``loopsb_spmv_f32`` ...) into the
+sm_100a kernels; like the reference wrappers they synchronise the stream before
+returning unless ``sync=False`` is passed (benchmark loops, multi-GPU overlap).
+Differences from the reference, both relaxations: ``y`` need not be zeroed
+beforehand (it is fully overwritten), and the merge-path preprocess is cached
+on the container instead of being rebuilt per call.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import _lib
+from ..container import bcsr_t, coo_t, csr_t, ell_t
+
+
+class timer_t:
+    """CUDA-event stopwatch with the reference's accessor names (util/timer.hxx)."""
+
+    def __init__(self, stream):
+        self._stream = stream
+        self._a = torch.cuda.Event(enable_timing=True)
+        self._b = torch.cuda.Event(enable_timing=True)
+
+    def start(self):
+        self._a.record(self._stream)
+
+    def stop(self):
+        self._b.record(self._stream)
+        self._b.synchronize()
+
+    def milliseconds(self) -> float:
+        return self._a.elapsed_time(self._b)
+
+    def seconds(self) -> float:
+        return self.milliseconds() / 1e3
+
+
+def _check_vec(name, t, n):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32
+            and t.is_contiguous() and t.numel() >= n):
+        raise ValueError(f"{name} must be a contiguous CUDA float32 tensor with >= {n} elements")
+
+
+def _run(container, schedule, values, cols, rows_idx, x, y, nrows, ncols, stream, sync, timed):
+    lib = _lib.load()
+    stream = stream or torch.cuda.current_stream()
+    _check_vec("x", x, ncols)
+    _check_vec("y", y, nrows)
+    plan = container.plan(schedule, stream)
+    timer = timer_t(stream) if (timed and sync) else None
+    if timer:
+        timer.start()
+    _lib.check(lib.loopsb_spmv_f32(plan.handle, _lib.ptr(values), _lib.ptr(cols), _lib.ptr(rows_idx),
+                                   _lib.ptr(x), _lib.ptr(y), nrows, ncols, _lib.stream_ptr(stream)),
+               "loopsb_spmv_f32")
+    if timer:
+        timer.stop()
+    elif sync:
+        stream.synchronize()
+    return timer
+
+
+def _csr(csr: csr_t, schedule, x, y, stream, sync, timed=False):
+    return _run(csr, schedule, csr.values, csr.indices, None, x, y, csr.rows, csr.cols, stream, sync, timed)
+
+
+def merge_path_flat(csr: csr_t, x, y, stream=None, sync=True):
+    return _csr(csr, _lib.SCHED_MERGE_PATH_FLAT, x, y, stream, sync, timed=True)
+
+
+def work_oriented(csr: csr_t, x, y, stream=None, sync=True):
+    _csr(csr, _lib.SCHED_WORK_ORIENTED, x, y, stream, sync)
+
+
+def thread_mapped(csr: csr_t, x, y, stream=None, sync=True):
+    _csr(csr, _lib.SCHED_THREAD_MAPPED, x, y, stream, sync)
+
+
+def group_mapped(csr: csr_t, x, y, stream=None, sync=True):
+    _csr(csr, _lib.SCHED_GROUP_MAPPED, x, y, stream, sync)
+
+
+def coo_thread_mapped(coo: coo_t, x, y, stream=None, sync=True):
+    return _run(coo, _lib.SCHED_THREAD_MAPPED, coo.values, coo.col_indices, coo.row_indices, x, y,
+                coo.rows, coo.cols, stream, sync, timed=True)
+
+
+def ell_thread_mapped(ell: ell_t, x, y, stream=None, sync=True):
+    _run(ell, _lib.SCHED_THREAD_MAPPED, ell.values, ell.indices, None, x, y, ell.rows, ell.cols,
+         stream, sync, timed=False)
+
+
+def ell_merge_path(ell: ell_t, x, y, stream=None, sync=True):
+    return _run(ell, _lib.SCHED_MERGE_PATH_FLAT, ell.values, ell.indices, None, x, y, ell.rows,
+                ell.cols, stream, sync, timed=True)
+
+
+def bcsr_thread_mapped(bcsr: bcsr_t, x, y, stream=None, sync=True):
+    """fp32 blocks: one thread per block-row (the reference kernel's map).
+    bf16 4x4 blocks: the tcgen05 tensor-core kernel (BASELINE config 4).
+    ``x`` must already be padded to ``num_block_cols * C`` (bcsr.padded_x)."""
+    lib = _lib.load()
+    stream = stream or torch.cuda.current_stream()
+    n_pad = bcsr.num_block_cols * bcsr.C
+    timer = timer_t(stream) if sync else None
+    if timer:
+        timer.start()
+    if bcsr.values.dtype == torch.float32:
+        _check_vec("x", x, n_pad)
+        _check_vec("y", y, bcsr.rows)
+        d = bcsr.layout().desc()
+        import ctypes as C
+        _lib.check(lib.loopsb_spmv_bcsr_f32(bcsr.R, bcsr.C, C.byref(d), _lib.ptr(bcsr.values),
+                                            _lib.ptr(bcsr.block_col_indices), _lib.ptr(x), _lib.ptr(y),
+                                            bcsr.rows, _lib.stream_ptr(stream)), "loopsb_spmv_bcsr_f32")
+    elif bcsr.values.dtype == torch.bfloat16:
+        if not (bcsr.R == 4 and bcsr.C == 4):
+            raise _lib.LoopsbError(_lib.ERR_UNSUPPORTED, "bcsr_thread_mapped", "bf16 path is 4x4 only")
+        if not (x.dtype == torch.bfloat16 and x.is_cuda and x.numel() >= n_pad):
+            raise ValueError("x must be a CUDA bfloat16 tensor padded to num_block_cols*4")
+        _check_vec("y", y, bcsr.rows)
+        plan = bcsr.plan(_lib.SCHED_THREAD_MAPPED, stream)
+        _lib.check(lib.loopsb_spmv_bcsr4x4_bf16(plan.handle, _lib.ptr(bcsr.values),
+                                                _lib.ptr(bcsr.block_col_indices), _lib.ptr(x),
+                                                _lib.ptr(y), bcsr.rows, _lib.stream_ptr(stream)),
+                   "loopsb_spmv_bcsr4x4_bf16")
+    else:
+        raise _lib.LoopsbError(_lib.ERR_UNSUPPORTED, "bcsr_thread_mapped", f"dtype {bcsr.values.dtype}")
+    if timer:
+        timer.stop()
+    return timer
+
+
+BY_NAME = {
+    "merge_path_flat": merge_path_flat,
+    "work_oriented": work_oriented,
+    "thread_mapped": thread_mapped,
+    "group_mapped": group_mapped,
+}

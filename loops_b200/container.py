@@ -1,0 +1,170 @@
+"""Owning sparse containers on the GPU, mirroring the reference's
+``csr_t / coo_t / ell_t / bcsr_t`` (reference include/loops/container/
+{csr,coo,ell,bcsr}.hxx): same array names, dtypes (int32 ids, fp32 values) and
+padding rules. Storage is torch tensors (device memory + streams are torch's
+job here); the compute never touches torch.
+
+Format conversions run on the host with numpy, like the reference's
+(``ell_t(csr)`` ell.hxx:113-145, ``bcsr_t(csr)`` bcsr.hxx:111-194,
+``coo_t(csr)`` coo.hxx:87-98); they are set-up code, not the SpMV hot path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .layout import csr as csr_layout, coo as coo_layout, ell as ell_layout, bcsr as bcsr_layout
+
+
+def _dev(a, dtype, device):
+    t = torch.as_tensor(np.ascontiguousarray(a), dtype=dtype)
+    return t.to(device) if device is not None else t
+
+
+class _planned:
+    """Caches one plan (the reference's preprocess_t) per schedule."""
+
+    def __init__(self):
+        self._plans = {}
+
+    def plan(self, schedule: int, stream=None):
+        from .plan import Plan
+        p = self._plans.get(schedule)
+        if p is None:
+            p = Plan(self.layout(), schedule, stream)
+            self._plans[schedule] = p
+        return p
+
+    def drop_plans(self):
+        for p in self._plans.values():
+            p.close()
+        self._plans.clear()
+
+
+class csr_t(_planned):
+    """rows, cols, nnzs; offsets[rows+1], indices[nnzs], values[nnzs]."""
+
+    def __init__(self, rows, cols, offsets, indices, values, device="cuda"):
+        super().__init__()
+        self.rows, self.cols = int(rows), int(cols)
+        self.offsets = _dev(offsets, torch.int32, device)
+        self.indices = _dev(indices, torch.int32, device)
+        self.values = _dev(values, torch.float32, device)
+        self.nnzs = int(self.indices.numel())
+        assert self.offsets.numel() == self.rows + 1
+
+    @classmethod
+    def from_tensors(cls, rows, cols, offsets, indices, values):
+        self = cls.__new__(cls)
+        _planned.__init__(self)
+        self.rows, self.cols = int(rows), int(cols)
+        self.offsets, self.indices, self.values = offsets, indices, values
+        self.nnzs = int(indices.numel())
+        return self
+
+    def layout(self):
+        return csr_layout(self.offsets, self.rows, self.nnzs)
+
+    def host(self):
+        return (self.offsets.cpu().numpy(), self.indices.cpu().numpy(), self.values.cpu().numpy())
+
+
+class coo_t(_planned):
+    """row_indices, col_indices, values, each [nnzs]."""
+
+    def __init__(self, rows, cols, row_indices, col_indices, values, device="cuda"):
+        super().__init__()
+        self.rows, self.cols = int(rows), int(cols)
+        self.row_indices = _dev(row_indices, torch.int32, device)
+        self.col_indices = _dev(col_indices, torch.int32, device)
+        self.values = _dev(values, torch.float32, device)
+        self.nnzs = int(self.values.numel())
+
+    @classmethod
+    def from_csr(cls, csr: csr_t):
+        off, idx, val = csr.host()
+        rows_of = np.repeat(np.arange(csr.rows, dtype=np.int32), np.diff(off))
+        return cls(csr.rows, csr.cols, rows_of, idx, val, device=csr.values.device)
+
+    def layout(self):
+        return coo_layout(self.nnzs)
+
+
+class ell_t(_planned):
+    """Row-major rows*pitch slabs; padding = column -1, value 0."""
+
+    SENTINEL = -1
+
+    def __init__(self, rows, cols, nnzs, pitch, indices, values, device="cuda"):
+        super().__init__()
+        self.rows, self.cols, self.nnzs, self.pitch = int(rows), int(cols), int(nnzs), int(pitch)
+        self.indices = _dev(indices, torch.int32, device)
+        self.values = _dev(values, torch.float32, device)
+
+    @classmethod
+    def from_csr(cls, csr: csr_t):
+        off, idx, val = csr.host()
+        deg = np.diff(off)
+        pitch = int(deg.max()) if csr.rows else 0
+        e_idx = np.full((csr.rows, pitch), cls.SENTINEL, dtype=np.int32)
+        e_val = np.zeros((csr.rows, pitch), dtype=np.float32)
+        if csr.nnzs:
+            r = np.repeat(np.arange(csr.rows), deg)
+            slot = np.arange(csr.nnzs) - np.repeat(off[:-1], deg)
+            e_idx[r, slot] = idx
+            e_val[r, slot] = val
+        return cls(csr.rows, csr.cols, csr.nnzs, pitch, e_idx.reshape(-1), e_val.reshape(-1),
+                   device=csr.values.device)
+
+    def layout(self):
+        return ell_layout(self.rows, self.pitch)
+
+
+class bcsr_t(_planned):
+    """R x C dense blocks: block_offsets[nbr+1], block_col_indices[nb],
+    values[nb*R*C] with values[b*R*C + i*C + j]; block columns ascending per
+    block-row; entries assigned (not accumulated); padding zero."""
+
+    def __init__(self, R, C, rows, cols, nnzs, block_offsets, block_col_indices, values,
+                 device="cuda", value_dtype=torch.float32):
+        super().__init__()
+        self.R, self.C = int(R), int(C)
+        self.rows, self.cols, self.nnzs = int(rows), int(cols), int(nnzs)
+        self.num_block_rows = (self.rows + self.R - 1) // self.R
+        self.num_block_cols = (self.cols + self.C - 1) // self.C
+        self.block_offsets = _dev(block_offsets, torch.int32, device)
+        self.block_col_indices = _dev(block_col_indices, torch.int32, device)
+        self.values = _dev(values, torch.float32, device).to(value_dtype)
+        self.num_blocks = int(self.block_col_indices.numel())
+
+    @classmethod
+    def from_csr(cls, csr: csr_t, R: int, C: int, value_dtype=torch.float32):
+        off, idx, val = csr.host()
+        rows, cols = csr.rows, csr.cols
+        nbr, nbc = (rows + R - 1) // R, (cols + C - 1) // C
+        r = np.repeat(np.arange(rows, dtype=np.int64), np.diff(off))
+        br, bc = r // R, idx.astype(np.int64) // C
+        key = br * max(nbc, 1) + bc
+        uniq, inv = np.unique(key, return_inverse=True)   # sorted: (br, bc) ascending
+        nb = int(uniq.size)
+        b_off = np.zeros(nbr + 1, dtype=np.int64)
+        np.add.at(b_off, (uniq // max(nbc, 1)) + 1, 1)
+        b_off = np.cumsum(b_off)
+        b_col = (uniq % max(nbc, 1)).astype(np.int32)
+        b_val = np.zeros(nb * R * C, dtype=np.float32)
+        b_val[inv * (R * C) + (r % R) * C + (idx % C)] = val   # assignment, last wins
+        return cls(R, C, rows, cols, csr.nnzs, b_off.astype(np.int32), b_col, b_val,
+                   device=csr.values.device, value_dtype=value_dtype)
+
+    def layout(self):
+        return bcsr_layout(self.block_offsets, self.num_block_rows, self.num_blocks)
+
+    def padded_x(self, x: torch.Tensor) -> torch.Tensor:
+        """x padded with zeros to num_block_cols*C (examples/spmv/bcsr_thread_mapped.cu:41)."""
+        n = self.num_block_cols * self.C
+        if x.numel() == n:
+            return x
+        out = torch.zeros(n, dtype=x.dtype, device=x.device)
+        out[: x.numel()] = x
+        return out

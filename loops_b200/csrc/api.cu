@@ -1,0 +1,463 @@
+// loops_b200/csrc/api.cu -- the C ABI declared in include/loopsb.h:
+// plan management (the reference's merge_path::preprocess_t generalised) and
+// SpMV dispatch by (schedule, layout kind).
+
+#include "common.cuh"
+#include "spmv_merge.cuh"
+#include "spmv_schedules.cuh"
+#include "bcsr_tc.cuh"
+
+#include <cstdarg>
+#include <mutex>
+#include <new>
+
+namespace loopsb {
+
+char* last_error_buffer() {
+  static thread_local char buf[512] = "";
+  return buf;
+}
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buffer(), 512, fmt, ap);
+  va_end(ap);
+}
+
+const device_props* current_device() {
+  static device_props cache[64];
+  static std::mutex mu;
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= 64) {
+    (void)cudaGetLastError();
+    set_error("no usable CUDA device: %s (loops-b200 has no CPU fallback)",
+              cudaGetErrorString(e));
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  device_props& p = cache[dev];
+  if (!p.valid) {
+    if (cudaDeviceGetAttribute(&p.sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&p.cc_major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&p.cc_minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&p.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("cudaDeviceGetAttribute failed on device %d", dev);
+      return nullptr;
+    }
+    p.valid = true;
+  }
+  return &p;
+}
+
+}  // namespace loopsb
+
+using namespace loopsb;
+
+// Merge-path SpMV geometry: 256-thread CTAs, 4 reference merge tiles (4096
+// items) per CTA tile, double-buffered stage, 2 CTAs per SM.
+namespace {
+constexpr int kMergeThreads = 256;
+constexpr int kMergeG = 4;
+constexpr int kMergeTile = kMergeG * mp::kRefItemsPerMergeTile;
+constexpr int kMergeStages = 2;
+constexpr int kMergeCtasPerSm = 2;
+using merge_shared_t = mp::merge_shared<kMergeThreads, kMergeTile, kMergeStages>;
+}  // namespace
+
+struct loopsb_plan {
+  loopsb_layout_t lay;
+  int schedule;
+  int device;
+  int sm_count;
+  // merge_path_flat
+  int2* coords = nullptr;     // S(b*1024), b = 0..M
+  long long M = 0;
+  int num_cta_tiles = 0;
+  int* carry_row = nullptr;
+  float* carry_val = nullptr;
+  // launch geometry of the SpMV kernel
+  int grid = 0;
+  int cta_threads = 0;
+  int smem_bytes = 0;
+  int launches = 1;
+  long long workspace_bytes = 0;
+  // bcsr tensor-core path
+  bcsr_tc::plan_data* tc = nullptr;
+};
+
+extern "C" {
+
+int loopsb_version(void) { return LOOPSB_VERSION; }
+
+const char* loopsb_status_string(int status) {
+  switch (status) {
+    case LOOPSB_OK: return "ok";
+    case LOOPSB_ERR_INVALID: return "invalid argument";
+    case LOOPSB_ERR_CUDA: return "CUDA error";
+    case LOOPSB_ERR_UNSUPPORTED: return "unsupported (schedule, layout, dtype)";
+    case LOOPSB_ERR_ALLOC: return "allocation failed";
+    default: return "unknown status";
+  }
+}
+
+const char* loopsb_last_error(void) { return last_error_buffer(); }
+
+int loopsb_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+  const device_props* p = current_device();
+  if (!p) return LOOPSB_ERR_CUDA;
+  if (sm_count) *sm_count = p->sm_count;
+  if (cc_major) *cc_major = p->cc_major;
+  if (cc_minor) *cc_minor = p->cc_minor;
+  return LOOPSB_OK;
+}
+
+int loopsb_work_oriented_grid(int32_t* grid_blocks) {
+  LOOPSB_REQUIRE(grid_blocks != nullptr, "grid_blocks is null");
+  const device_props* p = current_device();
+  if (!p) return LOOPSB_ERR_CUDA;
+  int per_sm = 0;
+  LOOPSB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+      &per_sm, sk::spmv_work_oriented_csr, sk::kWorkThreads, 0));
+  if (per_sm < 1) per_sm = 1;
+  *grid_blocks = per_sm * p->sm_count;
+  return LOOPSB_OK;
+}
+
+int loopsb_plan_destroy(loopsb_plan_t* plan) {
+  if (!plan) return LOOPSB_OK;
+  if (plan->coords) cudaFree(plan->coords);
+  if (plan->carry_row) cudaFree(plan->carry_row);
+  if (plan->carry_val) cudaFree(plan->carry_val);
+  if (plan->tc) bcsr_tc::destroy(plan->tc);
+  delete plan;
+  return LOOPSB_OK;
+}
+
+int loopsb_plan_create(loopsb_plan_t** out, const loopsb_layout_t* lay,
+                       int schedule, void* stream) {
+  LOOPSB_REQUIRE(out != nullptr && lay != nullptr, "null argument");
+  *out = nullptr;
+  LOOPSB_REQUIRE(lay->num_tiles >= 0 && lay->num_atoms >= 0, "negative sizes");
+  LOOPSB_REQUIRE(schedule >= LOOPSB_SCHED_MERGE_PATH_FLAT &&
+                     schedule <= LOOPSB_SCHED_GROUP_MAPPED,
+                 "unknown schedule");
+  if (is_offsets_kind(lay->kind))
+    LOOPSB_REQUIRE(lay->offsets != nullptr, "offsets-kind layout without offsets");
+  if (is_pitch_kind(lay->kind))
+    LOOPSB_REQUIRE(lay->pitch >= 0, "negative pitch");
+  LOOPSB_REQUIRE((long long)lay->num_tiles + (long long)lay->num_atoms < 0x7fffffffLL,
+                 "tiles + atoms must stay below 2^31");
+  const device_props* dp = current_device();
+  if (!dp) return LOOPSB_ERR_CUDA;
+  cudaStream_t s = as_stream(stream);
+
+  loopsb_plan* p = new (std::nothrow) loopsb_plan();
+  if (!p) { set_error("host allocation failed"); return LOOPSB_ERR_ALLOC; }
+  p->lay = *lay;
+  p->schedule = schedule;
+  p->sm_count = dp->sm_count;
+  cudaGetDevice(&p->device);
+  const int T = lay->num_tiles, A = lay->num_atoms;
+
+  auto fail = [&](int code) { loopsb_plan_destroy(p); return code; };
+
+  if (schedule == LOOPSB_SCHED_MERGE_PATH_FLAT) {
+    const bool array_ends = lay->kind == LOOPSB_LAYOUT_CSR;
+    if (!array_ends && lay->kind != LOOPSB_LAYOUT_ELL) {
+      set_error("merge_path_flat SpMV exists for CSR and ELL (reference has no other)");
+      return fail(LOOPSB_ERR_UNSUPPORTED);
+    }
+    const long long W = (long long)T + A;
+    p->M = (W + mp::kRefItemsPerMergeTile - 1) / mp::kRefItemsPerMergeTile;
+    p->num_cta_tiles = int((p->M + kMergeG - 1) / kMergeG);
+    p->cta_threads = kMergeThreads;
+    p->smem_bytes = int(sizeof(merge_shared_t));
+    p->launches = 2;
+    int grid = kMergeCtasPerSm * dp->sm_count;
+    if (grid > p->num_cta_tiles) grid = p->num_cta_tiles;
+    p->grid = grid;
+    if (p->M > 0) {
+      const size_t cbytes = size_t(p->M + 1) * sizeof(int2);
+      const size_t nct = size_t(p->num_cta_tiles);
+      if (cudaMalloc(&p->coords, cbytes) != cudaSuccess ||
+          cudaMalloc(&p->carry_row, nct * sizeof(int)) != cudaSuccess ||
+          cudaMalloc(&p->carry_val, nct * sizeof(float)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("device allocation of the merge-path workspace failed");
+        return fail(LOOPSB_ERR_ALLOC);
+      }
+      p->workspace_bytes = (long long)(cbytes + nct * 8);
+      const int threads = 128;
+      const int blocks = int((p->M + 1 + threads - 1) / threads);
+      if (array_ends)
+        mp::merge_coords_kernel<true><<<blocks, threads, 0, s>>>(
+            lay->offsets + 1, 0, T, A, mp::kRefItemsPerMergeTile, int(p->M), p->coords);
+      else
+        mp::merge_coords_kernel<false><<<blocks, threads, 0, s>>>(
+            nullptr, lay->pitch, T, A, mp::kRefItemsPerMergeTile, int(p->M), p->coords);
+      if (cudaGetLastError() != cudaSuccess) {
+        set_error("merge_coords_kernel launch failed");
+        return fail(LOOPSB_ERR_CUDA);
+      }
+      auto kern_a = mp::spmv_merge_kernel<kMergeThreads, kMergeTile, kMergeStages, true>;
+      auto kern_p = mp::spmv_merge_kernel<kMergeThreads, kMergeTile, kMergeStages, false>;
+      if (cudaFuncSetAttribute(kern_a, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes) != cudaSuccess ||
+          cudaFuncSetAttribute(kern_p, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes) != cudaSuccess) {
+        set_error("cannot opt in to %d bytes of dynamic shared memory", p->smem_bytes);
+        (void)cudaGetLastError();
+        return fail(LOOPSB_ERR_CUDA);
+      }
+    }
+  } else if (schedule == LOOPSB_SCHED_THREAD_MAPPED) {
+    if (!(lay->kind == LOOPSB_LAYOUT_CSR || lay->kind == LOOPSB_LAYOUT_COO ||
+          lay->kind == LOOPSB_LAYOUT_ELL || lay->kind == LOOPSB_LAYOUT_BCSR)) {
+      set_error("thread_mapped SpMV exists for CSR, COO, ELL and BCSR here");
+      return fail(LOOPSB_ERR_UNSUPPORTED);
+    }
+    p->cta_threads = 128;
+    p->grid = (T + 127) / 128;
+    p->launches = lay->kind == LOOPSB_LAYOUT_COO ? 2 : 1;
+    if (lay->kind == LOOPSB_LAYOUT_BCSR) {
+      int rc = bcsr_tc::create(&p->tc, lay, dp->sm_count, s);
+      if (rc != LOOPSB_OK) return fail(rc);
+      p->workspace_bytes = bcsr_tc::workspace_bytes(p->tc);
+    }
+  } else if (schedule == LOOPSB_SCHED_GROUP_MAPPED) {
+    if (lay->kind != LOOPSB_LAYOUT_CSR) {
+      set_error("group_mapped SpMV exists for CSR (reference has no other)");
+      return fail(LOOPSB_ERR_UNSUPPORTED);
+    }
+    p->cta_threads = sk::kGroupThreads;
+    p->grid = (T + sk::kGroupThreads - 1) / sk::kGroupThreads;
+  } else {  // work_oriented
+    if (lay->kind != LOOPSB_LAYOUT_CSR) {
+      set_error("work_oriented SpMV exists for CSR (reference has no other)");
+      return fail(LOOPSB_ERR_UNSUPPORTED);
+    }
+    int g = 0;
+    int rc = loopsb_work_oriented_grid(&g);
+    if (rc != LOOPSB_OK) return fail(rc);
+    p->cta_threads = sk::kWorkThreads;
+    p->grid = g;
+    p->launches = 2;  // memset + kernel
+  }
+  *out = p;
+  return LOOPSB_OK;
+}
+
+int loopsb_plan_info(const loopsb_plan_t* plan, loopsb_plan_info_t* info) {
+  LOOPSB_REQUIRE(plan != nullptr && info != nullptr, "null argument");
+  memset(info, 0, sizeof(*info));
+  info->schedule = plan->schedule;
+  info->layout_kind = plan->lay.kind;
+  info->threads_per_block = 128;
+  info->items_per_thread = plan->schedule == LOOPSB_SCHED_MERGE_PATH_FLAT ? 8 : 1;
+  info->num_merge_tiles = plan->M;
+  info->grid_blocks = plan->grid;
+  info->cta_threads = plan->cta_threads;
+  info->launches_per_spmv = plan->launches;
+  info->smem_bytes = plan->smem_bytes;
+  info->workspace_bytes = plan->workspace_bytes;
+  return LOOPSB_OK;
+}
+
+int loopsb_plan_merge_coords_host(const loopsb_plan_t* plan, int32_t* host_xy,
+                                  int64_t capacity_pairs) {
+  LOOPSB_REQUIRE(plan != nullptr && host_xy != nullptr, "null argument");
+  LOOPSB_REQUIRE(plan->schedule == LOOPSB_SCHED_MERGE_PATH_FLAT, "not a merge-path plan");
+  LOOPSB_REQUIRE(capacity_pairs >= plan->M + 1, "host buffer too small");
+  if (plan->M == 0) { host_xy[0] = 0; host_xy[1] = 0; return LOOPSB_OK; }
+  LOOPSB_CUDA_TRY(cudaDeviceSynchronize());
+  LOOPSB_CUDA_TRY(cudaMemcpy(host_xy, plan->coords, size_t(plan->M + 1) * sizeof(int2),
+                             cudaMemcpyDeviceToHost));
+  return LOOPSB_OK;
+}
+
+int loopsb_spmv_f32(loopsb_plan_t* plan, const float* values,
+                    const int32_t* col_indices, const int32_t* row_indices,
+                    const float* x, float* y, int32_t num_rows,
+                    int32_t num_cols, void* stream) {
+  LOOPSB_REQUIRE(plan != nullptr, "plan is null");
+  LOOPSB_REQUIRE(num_rows >= 0 && num_cols >= 0, "negative dimensions");
+  const loopsb_layout_t& lay = plan->lay;
+  const int T = lay.num_tiles, A = lay.num_atoms;
+  LOOPSB_REQUIRE(num_rows == 0 || y != nullptr, "y is null");
+  LOOPSB_REQUIRE(A == 0 || (values && col_indices && x), "null matrix / x pointer");
+  cudaStream_t s = as_stream(stream);
+  if (num_rows == 0) return LOOPSB_OK;
+  if (A == 0) {  // nothing stored: y = 0
+    LOOPSB_CUDA_TRY(cudaMemsetAsync(y, 0, size_t(num_rows) * sizeof(float), s));
+    return LOOPSB_OK;
+  }
+
+  switch (plan->schedule) {
+    case LOOPSB_SCHED_MERGE_PATH_FLAT: {
+      LOOPSB_REQUIRE(T == num_rows, "layout tiles must equal num_rows");
+      const int nct = plan->num_cta_tiles;
+      if (lay.kind == LOOPSB_LAYOUT_CSR) {
+        mp::spmv_merge_kernel<kMergeThreads, kMergeTile, kMergeStages, true>
+            <<<plan->grid, kMergeThreads, plan->smem_bytes, s>>>(
+                lay.offsets + 1, 0, col_indices, values, x, y, plan->coords,
+                int(plan->M), kMergeG, T, A, nct, plan->carry_row, plan->carry_val);
+      } else {
+        mp::spmv_merge_kernel<kMergeThreads, kMergeTile, kMergeStages, false>
+            <<<plan->grid, kMergeThreads, plan->smem_bytes, s>>>(
+                nullptr, lay.pitch, col_indices, values, x, y, plan->coords,
+                int(plan->M), kMergeG, T, A, nct, plan->carry_row, plan->carry_val);
+      }
+      LOOPSB_CUDA_TRY(cudaGetLastError());
+      mp::spmv_merge_fixup_kernel<<<(nct + 255) / 256, 256, 0, s>>>(
+          plan->carry_row, plan->carry_val, nct, T, y);
+      LOOPSB_CUDA_TRY(cudaGetLastError());
+      return LOOPSB_OK;
+    }
+    case LOOPSB_SCHED_THREAD_MAPPED: {
+      if (lay.kind == LOOPSB_LAYOUT_CSR) {
+        LOOPSB_REQUIRE(T == num_rows, "layout tiles must equal num_rows");
+        sk::spmv_thread_mapped_csr<<<plan->grid, 128, 0, s>>>(
+            lay.offsets, col_indices, values, x, y, num_rows);
+      } else if (lay.kind == LOOPSB_LAYOUT_COO) {
+        LOOPSB_REQUIRE(row_indices != nullptr, "COO needs row_indices");
+        LOOPSB_CUDA_TRY(cudaMemsetAsync(y, 0, size_t(num_rows) * sizeof(float), s));
+        sk::spmv_coo_thread_mapped<<<(A + 127) / 128, 128, 0, s>>>(
+            row_indices, col_indices, values, x, y, A);
+      } else if (lay.kind == LOOPSB_LAYOUT_ELL) {
+        LOOPSB_REQUIRE(T == num_rows, "layout tiles must equal num_rows");
+        sk::spmv_ell_thread_mapped<<<plan->grid, 128, 0, s>>>(
+            col_indices, values, x, y, num_rows, lay.pitch);
+      } else {
+        set_error("use loopsb_spmv_bcsr_f32 / loopsb_spmv_bcsr4x4_bf16 for BCSR");
+        return LOOPSB_ERR_UNSUPPORTED;
+      }
+      LOOPSB_CUDA_TRY(cudaGetLastError());
+      return LOOPSB_OK;
+    }
+    case LOOPSB_SCHED_GROUP_MAPPED: {
+      LOOPSB_REQUIRE(T == num_rows, "layout tiles must equal num_rows");
+      sk::spmv_group_mapped_csr<<<plan->grid, sk::kGroupThreads, 0, s>>>(
+          lay.offsets, col_indices, values, x, y, num_rows);
+      LOOPSB_CUDA_TRY(cudaGetLastError());
+      return LOOPSB_OK;
+    }
+    case LOOPSB_SCHED_WORK_ORIENTED: {
+      LOOPSB_REQUIRE(T == num_rows, "layout tiles must equal num_rows");
+      LOOPSB_CUDA_TRY(cudaMemsetAsync(y, 0, size_t(num_rows) * sizeof(float), s));
+      sk::spmv_work_oriented_csr<<<plan->grid, sk::kWorkThreads, 0, s>>>(
+          lay.offsets, col_indices, values, x, y, num_rows, A);
+      LOOPSB_CUDA_TRY(cudaGetLastError());
+      return LOOPSB_OK;
+    }
+    default:
+      set_error("unknown schedule in plan");
+      return LOOPSB_ERR_INVALID;
+  }
+}
+
+int loopsb_spmv_bcsr_f32(int32_t R, int32_t C, const loopsb_layout_t* lay,
+                         const float* values, const int32_t* block_col_indices,
+                         const float* x_padded, float* y, int32_t num_rows,
+                         void* stream) {
+  LOOPSB_REQUIRE(lay != nullptr && lay->kind == LOOPSB_LAYOUT_BCSR, "BCSR layout required");
+  LOOPSB_REQUIRE(lay->offsets != nullptr, "block offsets are null");
+  LOOPSB_REQUIRE(num_rows >= 0, "negative rows");
+  if (current_device() == nullptr) return LOOPSB_ERR_CUDA;
+  if (num_rows == 0) return LOOPSB_OK;
+  LOOPSB_REQUIRE(y != nullptr, "y is null");
+  const int br = lay->num_tiles;
+  LOOPSB_REQUIRE(lay->num_atoms == 0 || (values && block_col_indices && x_padded),
+                 "null matrix / x pointer");
+  cudaStream_t s = as_stream(stream);
+  const int grid = (br + 127) / 128;
+  if (grid == 0) return LOOPSB_OK;
+  if (R == 2 && C == 2)
+    sk::spmv_bcsr_thread_mapped<2, 2><<<grid, 128, 0, s>>>(lay->offsets, block_col_indices, values, x_padded, y, br, num_rows);
+  else if (R == 3 && C == 3)
+    sk::spmv_bcsr_thread_mapped<3, 3><<<grid, 128, 0, s>>>(lay->offsets, block_col_indices, values, x_padded, y, br, num_rows);
+  else if (R == 4 && C == 4)
+    sk::spmv_bcsr_thread_mapped<4, 4><<<grid, 128, 0, s>>>(lay->offsets, block_col_indices, values, x_padded, y, br, num_rows);
+  else {
+    set_error("BCSR block shape %dx%d not instantiated (2x2, 3x3, 4x4)", R, C);
+    return LOOPSB_ERR_UNSUPPORTED;
+  }
+  LOOPSB_CUDA_TRY(cudaGetLastError());
+  return LOOPSB_OK;
+}
+
+int loopsb_spmv_bcsr4x4_bf16(loopsb_plan_t* plan, const uint16_t* values_bf16,
+                             const int32_t* block_col_indices,
+                             const uint16_t* x_bf16_padded, float* y,
+                             int32_t num_rows, void* stream) {
+  LOOPSB_REQUIRE(plan != nullptr && plan->tc != nullptr,
+                 "plan was not created from a BCSR layout with thread_mapped");
+  return bcsr_tc::run(plan->tc, &plan->lay, values_bf16, block_col_indices,
+                      x_bf16_padded, y, num_rows, as_stream(stream));
+}
+
+int loopsb_spmv_csr_host_f32(int schedule, int32_t num_rows, int32_t num_cols,
+                             int32_t nnz, const int32_t* host_offsets,
+                             const int32_t* host_indices,
+                             const float* host_values, const float* host_x,
+                             float* host_y, float* kernel_ms) {
+  LOOPSB_REQUIRE(num_rows >= 0 && num_cols >= 0 && nnz >= 0, "negative sizes");
+  LOOPSB_REQUIRE(host_offsets && (nnz == 0 || (host_indices && host_values)) &&
+                     (num_cols == 0 || host_x) && (num_rows == 0 || host_y),
+                 "null host pointer");
+  if (current_device() == nullptr) return LOOPSB_ERR_CUDA;
+  int *d_off = nullptr, *d_idx = nullptr;
+  float *d_val = nullptr, *d_x = nullptr, *d_y = nullptr;
+  loopsb_plan_t* plan = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = LOOPSB_OK;
+  auto cleanup = [&]() {
+    if (plan) loopsb_plan_destroy(plan);
+    cudaFree(d_off); cudaFree(d_idx); cudaFree(d_val); cudaFree(d_x); cudaFree(d_y);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  };
+#define HOST_TRY(expr)                                                        \
+  do {                                                                        \
+    cudaError_t e__ = (expr);                                                 \
+    if (e__ != cudaSuccess) {                                                 \
+      set_error("%s failed: %s", #expr, cudaGetErrorString(e__));             \
+      cleanup();                                                              \
+      return LOOPSB_ERR_CUDA;                                                 \
+    }                                                                         \
+  } while (0)
+  HOST_TRY(cudaMalloc(&d_off, size_t(num_rows + 1) * 4));
+  HOST_TRY(cudaMalloc(&d_idx, size_t(nnz ? nnz : 1) * 4));
+  HOST_TRY(cudaMalloc(&d_val, size_t(nnz ? nnz : 1) * 4));
+  HOST_TRY(cudaMalloc(&d_x, size_t(num_cols ? num_cols : 1) * 4));
+  HOST_TRY(cudaMalloc(&d_y, size_t(num_rows ? num_rows : 1) * 4));
+  HOST_TRY(cudaMemcpy(d_off, host_offsets, size_t(num_rows + 1) * 4, cudaMemcpyHostToDevice));
+  if (nnz) {
+    HOST_TRY(cudaMemcpy(d_idx, host_indices, size_t(nnz) * 4, cudaMemcpyHostToDevice));
+    HOST_TRY(cudaMemcpy(d_val, host_values, size_t(nnz) * 4, cudaMemcpyHostToDevice));
+  }
+  if (num_cols)
+    HOST_TRY(cudaMemcpy(d_x, host_x, size_t(num_cols) * 4, cudaMemcpyHostToDevice));
+  loopsb_layout_t lay{};
+  lay.kind = LOOPSB_LAYOUT_CSR;
+  lay.num_tiles = num_rows;
+  lay.num_atoms = nnz;
+  lay.offsets = d_off;
+  rc = loopsb_plan_create(&plan, &lay, schedule, nullptr);
+  if (rc != LOOPSB_OK) { cleanup(); return rc; }
+  HOST_TRY(cudaEventCreate(&e0));
+  HOST_TRY(cudaEventCreate(&e1));
+  HOST_TRY(cudaEventRecord(e0, 0));
+  rc = loopsb_spmv_f32(plan, d_val, d_idx, nullptr, d_x, d_y, num_rows, num_cols, nullptr);
+  if (rc != LOOPSB_OK) { cleanup(); return rc; }
+  HOST_TRY(cudaEventRecord(e1, 0));
+  HOST_TRY(cudaEventSynchronize(e1));
+  if (kernel_ms) HOST_TRY(cudaEventElapsedTime(kernel_ms, e0, e1));
+  if (num_rows)
+    HOST_TRY(cudaMemcpy(host_y, d_y, size_t(num_rows) * 4, cudaMemcpyDeviceToHost));
+#undef HOST_TRY
+  cleanup();
+  return LOOPSB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,331 @@
+// loops_b200/csrc/spmv_schedules.cuh -- SpMV kernels for the thread_mapped,
+// group_mapped and work_oriented schedules on CSR, plus the COO / ELL / BCSR
+// thread_mapped kernels. Each keeps the reference's thread->work map (so the
+// index streams of include/loops/schedule/*.hxx describe them) and changes how
+// the data moves:
+//
+//   thread_mapped (ref algorithms/spmv/thread_mapped.cuh:27-56)
+//       sequential left-to-right dot per row with un-fused mul/add: y is
+//       bit-identical to the reference CPU validator (util/reference.hxx:61-76).
+//   group_mapped  (ref group_mapped.cuh:27-61, block_mapped<128>)
+//       the block's 129 row offsets arrive by one bulk async copy; the prefix
+//       sums the reference builds with a CG scan ARE those offsets minus the
+//       first; the block's atoms are one contiguous, coalesced range; per-atom
+//       atomics to y are replaced by a warp-shuffle segmented reduce into 128
+//       shared accumulators and one coalesced store.
+//   work_oriented (ref work_oriented.cuh:35-89)
+//       the two diagonal searches of every thread run on a row-offset window
+//       staged in shared memory by a bulk async copy (block-level coordinates
+//       bound the window); commit rules (first complete row / later rows /
+//       remainder) follow the reference, y is zeroed by the library first.
+//   coo_thread_mapped (ref coo_thread_mapped.cuh:37-51)
+//       one thread per nonzero; equal-row runs inside a warp are reduced with
+//       shuffles before one atomic per run.
+//   ell_thread_mapped (ref ell_thread_mapped.cuh:28-43), bcsr_thread_mapped
+//       (ref bcsr_thread_mapped.cuh:36-74): same maps, read-only-path loads.
+#pragma once
+
+#include "common.cuh"
+
+#include <loops/util/tma.hxx>
+
+namespace loopsb {
+namespace sk {
+
+// ------------------------------------------------------------------ thread --
+__global__ void __launch_bounds__(128)
+    spmv_thread_mapped_csr(const int* __restrict__ offsets,
+                           const int* __restrict__ indices,
+                           const float* __restrict__ values,
+                           const float* __restrict__ x, float* __restrict__ y,
+                           int rows) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < rows;
+       row += stride) {
+    int k = __ldg(offsets + row);
+    const int end = __ldg(offsets + row + 1);
+    float sum = 0.0f;
+    // four independent (index -> x) chains in flight, adds stay in order
+    for (; k + 4 <= end; k += 4) {
+      const int c0 = __ldg(indices + k), c1 = __ldg(indices + k + 1);
+      const int c2 = __ldg(indices + k + 2), c3 = __ldg(indices + k + 3);
+      const float v0 = __ldg(values + k), v1 = __ldg(values + k + 1);
+      const float v2 = __ldg(values + k + 2), v3 = __ldg(values + k + 3);
+      const float x0 = __ldg(x + c0), x1 = __ldg(x + c1);
+      const float x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+      sum = __fadd_rn(sum, __fmul_rn(v0, x0));
+      sum = __fadd_rn(sum, __fmul_rn(v1, x1));
+      sum = __fadd_rn(sum, __fmul_rn(v2, x2));
+      sum = __fadd_rn(sum, __fmul_rn(v3, x3));
+    }
+    for (; k < end; ++k)
+      sum = __fadd_rn(sum, __fmul_rn(__ldg(values + k), __ldg(x + __ldg(indices + k))));
+    y[row] = sum;
+  }
+}
+
+// ------------------------------------------------------------------- group --
+// Sum `v` over runs of equal `key` among consecutive lanes; the first lane of
+// each run ends up with the run total.
+__device__ __forceinline__ float warp_run_sum(float v, int key, unsigned mask) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float ov = __shfl_down_sync(mask, v, d);
+    const int ok = __shfl_down_sync(mask, key, d);
+    if (lane + d < 32 && ok == key) v += ov;
+  }
+  return v;
+}
+
+constexpr int kGroupThreads = 128;
+
+__global__ void __launch_bounds__(kGroupThreads)
+    spmv_group_mapped_csr(const int* __restrict__ offsets,
+                          const int* __restrict__ indices,
+                          const float* __restrict__ values,
+                          const float* __restrict__ x, float* __restrict__ y,
+                          int rows) {
+  __shared__ __align__(16) int offs[kGroupThreads + 4];  // offsets[base..base+len]
+  __shared__ float acc[kGroupThreads];
+  __shared__ unsigned long long bar;
+  const int r = threadIdx.x;
+  const int base = blockIdx.x * kGroupThreads;
+  int len = rows - base;
+  if (len > kGroupThreads) len = kGroupThreads;
+  const int need = len + 1;
+  const int* src = offsets + base;
+  const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+  const int bulk = aligned ? (need & ~3) : 0;
+  uint64_t* mb = reinterpret_cast<uint64_t*>(&bar);
+  if (r == 0) {
+    loops::tma::barrier_init(mb, 1);
+    if (bulk > 0) {
+      loops::tma::barrier_arrive_expect_tx(mb, 4u * bulk);
+      loops::tma::bulk_g2s(offs, src, 4u * bulk, mb);
+    }
+  }
+  acc[r] = 0.0f;
+  for (int i = bulk + r; i < need; i += kGroupThreads) offs[i] = __ldg(src + i);
+  __syncthreads();
+  if (bulk > 0) loops::tma::barrier_wait(mb, 0);
+  __syncthreads();
+
+  const int first_atom = offs[0];
+  const int total = offs[len] - first_atom;  // == tile_aggregates of the block
+  int vt = 0;                                // tiles are visited in order
+  for (int vbase = 0; vbase < total; vbase += kGroupThreads) {
+    const int v = vbase + r;
+    const bool live = v < total;
+    float p = 0.0f;
+    int key = -1;
+    if (live) {
+      // upper_bound over the prefix (offs[i] - first_atom), resumed at vt
+      int lo = vt, cnt = len - vt;
+      while (cnt > 0) {
+        const int half = cnt >> 1;
+        if (!(v < offs[lo + half] - first_atom)) { lo += half + 1; cnt -= half + 1; }
+        else cnt = half;
+      }
+      vt = lo - 1;
+      key = vt;
+      const int nz = first_atom + v;
+      p = __fmul_rn(__ldg(values + nz), __ldg(x + __ldg(indices + nz)));
+    }
+    const float run = warp_run_sum(p, key, 0xffffffffu);
+    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    if (live && ((r & 31) == 0 || prev != key)) atomicAdd(&acc[key], run);
+  }
+  __syncthreads();
+  if (r < len) y[base + r] = acc[r];
+}
+
+// ----------------------------------------------------------- work oriented --
+constexpr int kWorkThreads = 128;
+constexpr int kWorkWindow = 6144;  // staged row ends per block (24 KB)
+
+__device__ __forceinline__ void work_search(long long d, const int* ends,
+                                            long long ends_first, long long lo_x,
+                                            long long hi_x, long long T,
+                                            long long A, long long& ox,
+                                            long long& oy) {
+  // ends[i - ends_first] == tile_end(i); search restricted to [lo_x, hi_x]
+  long long lo = d - A; if (lo < 0) lo = 0;
+  long long hi = d < T ? d : T;
+  if (lo < lo_x) lo = lo_x;
+  if (hi > hi_x) hi = hi_x;
+  const long long x_min = lo;
+  while (lo < hi) {
+    const long long mid = lo + ((hi - lo) >> 1);
+    if ((long long)ends[mid - ends_first] <= d - mid - 1) lo = mid + 1; else hi = mid;
+  }
+  if (hi < x_min) lo = x_min;
+  ox = lo < T ? lo : T;
+  oy = d - lo;
+}
+
+__global__ void __launch_bounds__(kWorkThreads)
+    spmv_work_oriented_csr(const int* __restrict__ offsets,
+                           const int* __restrict__ indices,
+                           const float* __restrict__ values,
+                           const float* __restrict__ x, float* __restrict__ y,
+                           int rows, int nnz) {
+  __shared__ __align__(16) int window[kWorkWindow + 8];
+  __shared__ long long bounds[4];
+  __shared__ unsigned long long bar;
+  const long long T = rows, A = nnz, W = T + A;
+  const long long N = (long long)gridDim.x * kWorkThreads;
+  const long long w = (W + N - 1) / N;
+  const int* row_end = offsets + 1;
+  const long long g = (long long)blockIdx.x * kWorkThreads + threadIdx.x;
+
+  // block-level coordinates: two threads, global search
+  if (threadIdx.x < 2) {
+    long long d = w * (long long)(blockIdx.x + threadIdx.x) * kWorkThreads;
+    if (d > W) d = W;
+    long long bx, by;
+    work_search(d, row_end, 0, 0, T, T, A, bx, by);
+    bounds[2 * threadIdx.x] = bx;
+    bounds[2 * threadIdx.x + 1] = by;
+  }
+  uint64_t* mb = reinterpret_cast<uint64_t*>(&bar);
+  if (threadIdx.x == 0) loops::tma::barrier_init(mb, 1);
+  __syncthreads();
+  const long long bx0 = bounds[0], bx1 = bounds[2];
+  // row ends needed by this block: indices bx0 .. min(bx1, T-1)
+  long long last = bx1 < T - 1 ? bx1 : T - 1;
+  const long long need = last - bx0 + 1;
+  const bool staged = need > 0 && need <= kWorkWindow;
+  const int* ends = row_end;
+  long long ends_first = 0;
+  if (staged) {
+    const int* src = row_end + bx0;
+    const int skew = int((reinterpret_cast<uintptr_t>(src) & 15u) >> 2);
+    const int covered = skew + int(need);
+    // stay inside the offsets array: it has T + 1 entries, row_end = offsets+1
+    const long long room = (long long)skew + (T - bx0);
+    int bulk = covered & ~3;
+    if (bulk > (room & ~3LL)) bulk = int(room & ~3LL);
+    if (threadIdx.x == 0 && bulk > 0) {
+      loops::tma::barrier_arrive_expect_tx(mb, 4u * bulk);
+      loops::tma::bulk_g2s(window, src - skew, 4u * bulk, mb);
+    }
+    for (int i = bulk + threadIdx.x; i < covered; i += kWorkThreads)
+      window[i] = __ldg(src - skew + i);
+    if (bulk > 0) loops::tma::barrier_wait(mb, 0);
+    __syncthreads();
+    ends = window + skew;
+    ends_first = bx0;
+  }
+
+  long long d0 = w * g; if (d0 > W) d0 = W;
+  long long d1 = d0 + w; if (d1 > W) d1 = W;
+  long long sx, sy, ex, ey;
+  work_search(d0, ends, ends_first, bx0, bx1, T, A, sx, sy);
+  work_search(d1, ends, ends_first, bx0, bx1, T, A, ex, ey);
+
+  float sum = 0.0f;
+  bool first_tile = true;
+  long long cur = sy;
+  for (long long row = sx; row < ex; ++row) {
+    const long long stop = ends[row - ends_first];
+    for (long long nz = cur; nz < stop; ++nz)
+      sum += __ldg(values + nz) * __ldg(x + __ldg(indices + nz));
+    cur = stop;
+    if (first_tile) {
+      if (sum != 0.0f) atomicAdd(y + row, sum);
+      first_tile = false;
+    } else {
+      y[row] = sum;
+    }
+    sum = 0.0f;
+  }
+  __syncthreads();
+  for (long long nz = cur; nz < ey; ++nz)
+    sum += __ldg(values + nz) * __ldg(x + __ldg(indices + nz));
+  if (sum != 0.0f) atomicAdd(y + ex, sum);
+}
+
+// --------------------------------------------------------------------- coo --
+__global__ void __launch_bounds__(128)
+    spmv_coo_thread_mapped(const int* __restrict__ row_indices,
+                           const int* __restrict__ col_indices,
+                           const float* __restrict__ values,
+                           const float* __restrict__ x, float* __restrict__ y,
+                           int nnz) {
+  const int stride = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  // whole warps iterate together so the shuffles stay convergent
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < nnz;
+       base += stride) {
+    const int a = base + lane;
+    const bool live = a < nnz;
+    int row = -1;
+    float p = 0.0f;
+    if (live) {
+      row = __ldg(row_indices + a);
+      p = __fmul_rn(__ldg(values + a), __ldg(x + __ldg(col_indices + a)));
+    }
+    const float run = warp_run_sum(p, row, 0xffffffffu);
+    const int prev = __shfl_up_sync(0xffffffffu, row, 1);
+    if (live && (lane == 0 || prev != row)) atomicAdd(y + row, run);
+  }
+}
+
+// --------------------------------------------------------------------- ell --
+__global__ void __launch_bounds__(128)
+    spmv_ell_thread_mapped(const int* __restrict__ indices,
+                           const float* __restrict__ values,
+                           const float* __restrict__ x, float* __restrict__ y,
+                           int rows, int pitch) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < rows;
+       row += stride) {
+    const long long first = (long long)row * pitch;
+    float sum = 0.0f;
+    for (int s = 0; s < pitch; ++s) {
+      const int col = __ldg(indices + first + s);
+      if (col >= 0)
+        sum = __fadd_rn(sum, __fmul_rn(__ldg(values + first + s), __ldg(x + col)));
+    }
+    y[row] = sum;
+  }
+}
+
+// -------------------------------------------------------------------- bcsr --
+template <int R, int C>
+__global__ void __launch_bounds__(128)
+    spmv_bcsr_thread_mapped(const int* __restrict__ block_offsets,
+                            const int* __restrict__ block_cols,
+                            const float* __restrict__ values,
+                            const float* __restrict__ x, float* __restrict__ y,
+                            int block_rows, int rows) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int br = blockIdx.x * blockDim.x + threadIdx.x; br < block_rows;
+       br += stride) {
+    float acc[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) acc[i] = 0.0f;
+    const int stop = __ldg(block_offsets + br + 1);
+    for (int b = __ldg(block_offsets + br); b < stop; ++b) {
+      const long long bc = __ldg(block_cols + b);
+      const float* blk = values + (long long)b * R * C;
+      float xs[C];
+#pragma unroll
+      for (int j = 0; j < C; ++j) xs[j] = __ldg(x + bc * C + j);
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < C; ++j)
+          acc[i] = __fadd_rn(acc[i], __fmul_rn(__ldg(blk + i * C + j), xs[j]));
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const long long row = (long long)br * R + i;
+      if (row < rows) y[row] = acc[i];
+    }
+  }
+}
+
+}  // namespace sk
+}  // namespace loopsb
