@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- CSR SpMV throughput (nnz/s) of the merge_path_flat hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one SpMV  y = A x  over the whole matrix.
+  N == 1 : BASELINE.json configs[1] -- synthetic power-law CSR, 2^20 rows,
+           2^25 nnz, fp32, merge_path_flat, one B200.
+  N  > 1 : BASELINE.json configs[4] -- 2^24 rows / 2^29 nnz row-partitioned over
+           the N ranks (contiguous row ranges, global column ids); every step is
+           one NCCL all-gather of the dense x shards followed by the local
+           merge-path SpMV. Total work is fixed as N grows ("strong").
+Inputs are generated in HBM (deterministic counter-based generator, x = the
+reference's recipe) and exceed the 126 MB L2 (272 MB of matrix per step), so
+consecutive timed steps cannot be served from cache ("l2": "inputs_exceed_l2").
+
+One JSON line on stdout (rank 0). `value` = device-timed whole-job nnz/s with
+inputs resident in HBM; `e2e` = the same through the public API with x coming
+from pinned host memory and y going back every step; `roofline` = algorithmic
+bytes / CUDA-event duration of the merge-path kernel alone (probes on the
+launching stream) against MEASURED_PEAKS.json; `cpu_baseline` = the reference's
+own CPU validator (oracle/_ref, built from its unmodified headers) on this
+box's host cores.
+
+`--impl reference` times that CPU validator as the reference arm, on all host
+threads (each thread runs the unmodified reference::spmv on a contiguous row
+slice), for the same config / metric / unit.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "csr_spmv_nnz_per_s"
+UNIT = "nnz/s"
+CFG2 = dict(rows=1 << 20, cols=1 << 20, nnz=1 << 25)
+CFG5 = dict(rows=1 << 24, cols=1 << 24, nnz=1 << 29)
+FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def algorithmic_bytes(rows, cols, nnz):
+    """nnz*(4+4) + (rows+1)*4 + cols*4 + rows*4 (x and y once)."""
+    return nnz * 8 + (rows + 1) * 4 + cols * 4 + rows * 4
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock / throttle reasons sampled DURING the timed region (NVML)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def report(self):
+        if not self.samples:
+            return None
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def ref_host_lib():
+    p = os.path.join(ROOT, "oracle", "_ref", "libloopsref_host.so")
+    return C.CDLL(p) if os.path.exists(p) else None
+
+
+def cpu_spmv_seconds(off, idx, val, x, rows, cols, reps, threads):
+    """Best-of-`reps` seconds per SpMV of the reference CPU validator
+    (oracle/_ref) or, if that library is absent, of the oracle port."""
+    import numpy as np
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    nnz = len(idx)
+    L = ref_host_lib()
+    if L is not None:
+        L.ref_time_spmv.restype = C.c_double
+        y = np.zeros(rows, np.float32)
+        return L.ref_time_spmv(rows, cols, nnz, P(off), P(idx), P(val), P(x), reps, threads, P(y)), "reference", y
+    so = os.path.join(ROOT, "oracle", "libloops_oracle.so")
+    if not os.path.exists(so):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    O = C.CDLL(so)
+    y = np.zeros(rows, np.float32)
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        O.orc_spmv_f32(rows, P(off), P(idx), P(val), P(x), P(y))
+        best = min(best, time.perf_counter() - t0)
+    return best, "port", y
+
+
+def make_inputs(cfg, device, row_begin=0, row_end=None):
+    from loops_b200 import generate as g
+    deg = g.powerlaw_degrees(cfg["rows"], cfg["nnz"], d_max=min(1024, cfg["cols"]))
+    off, idx, val = g.synth_csr(cfg["rows"], cfg["cols"], cfg["nnz"], device=device, degrees=deg,
+                                row_begin=row_begin, row_end=row_end)
+    return deg, off, idx, val
+
+
+def run_reference_arm(args, rank, world):
+    """Reference arm: the reference's CPU SpMV on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    from loops_b200 import generate as g
+    cfg = CFG2 if args.gpus == 1 else CFG5
+    # bounded sample: the first 2^20 rows / 2^25 nnz of the workload (that IS
+    # the whole N=1 workload; for N>1 it is 1/16 of the rows, same generator)
+    sample = dict(CFG2) if args.gpus == 1 else dict(rows=1 << 20, cols=cfg["cols"], nnz=None)
+    if args.gpus == 1:
+        _, off, idx, val = make_inputs(cfg, "cpu")
+    else:
+        deg = g.powerlaw_degrees(cfg["rows"], cfg["nnz"], d_max=1024)
+        off, idx, val = g.synth_csr(cfg["rows"], cfg["cols"], cfg["nnz"], degrees=deg, row_begin=0,
+                                    row_end=sample["rows"])
+    x = g.x_recipe(cfg["cols"]).numpy()
+    off, idx, val = off.numpy(), idx.numpy(), val.numpy()
+    rows, nnz = len(off) - 1, len(idx)
+    threads = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_spmv_seconds(off, idx, val, x, rows, cfg["cols"], 1, threads)
+    t0 = time.perf_counter()
+    sec, kind, _ = cpu_spmv_seconds(off, idx, val, x, rows, cfg["cols"], max(args.steps, 1), threads)
+    wall = time.perf_counter() - t0
+    value = nnz / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{rows} rows / {nnz} nnz of the workload, best of {args.steps} "
+                                   f"passes, {threads} threads x unmodified reference::spmv on row slices"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    if n == 1:
+        return {"workload": "synthetic power-law CSR 2^20 rows / 2^25 nnz fp32, merge_path_flat (BASELINE configs[1])",
+                "rows": CFG2["rows"], "nnz": CFG2["nnz"], "schedule": "merge_path_flat", "layout": "csr",
+                "degree_law": "P(d)~d^-2.1, d in [1,1024], seeded row order", "columns": "stratified hash, unique ascending",
+                "l2": "inputs_exceed_l2", "partition": "none"}
+    return {"workload": "synthetic power-law CSR 2^24 rows / 2^29 nnz fp32, merge_path_flat, row-partitioned, "
+                        "one NCCL all-gather of x per step (BASELINE configs[4])",
+            "rows": CFG5["rows"], "nnz": CFG5["nnz"], "schedule": "merge_path_flat", "layout": "csr",
+            "l2": "inputs_exceed_l2", "partition": f"row{n}", "collective": "nccl all_gather(x)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if args.steps > 20:
+            args.steps = 5          # CPU passes are ~0.1-1 s each; keep the arm within minutes
+        args.warmup = min(args.warmup, 2)
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from loops_b200 import _lib, csr_t, generate as g
+    from loops_b200.algorithms import spmv
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: loops-b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    N = args.gpus
+    if world != N:
+        if world == 1 and N > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    if N > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = CFG2 if N == 1 else CFG5
+    rows, cols, nnz = cfg["rows"], cfg["cols"], cfg["nnz"]
+    r0, r1 = (rows * rank) // N, (rows * (rank + 1)) // N
+    deg, off, idx, val = make_inputs(cfg, dev, r0, r1)
+    A = csr_t.from_tensors(r1 - r0, cols, off, idx, val)
+    x_full = g.x_recipe(cols, device=dev)
+    x_shard = x_full[(cols * rank) // N: (cols * (rank + 1)) // N].clone()
+    y = torch.empty(r1 - r0, dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream()
+    plan = A.plan(_lib.SCHED_MERGE_PATH_FLAT, stream)
+    info = plan.info()
+    torch.cuda.synchronize()
+
+    def step():
+        if N > 1:
+            dist.all_gather_into_tensor(x_full, x_shard)
+        spmv.merge_path_flat(A, x_full, y, stream=stream, sync=False)
+
+    def barrier():
+        if N > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream ----
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    if N > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = nnz / (ms_step * 1e-3)
+
+    # ---- kernel-only probes (second pass; not part of `value`) ----
+    plan.probe_begin(args.steps)
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    kernel_ms = plan.probe_collect(args.steps)
+    local_nnz = int(idx.numel())
+    local_bytes = algorithmic_bytes(r1 - r0, cols, local_nnz)
+    peak, peak_src = measured_peak()
+    k_ms = float(np.mean(kernel_ms))
+    achieved = local_bytes / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "spmv_merge_kernel<256,4096,2,true>",
+                "kernel_ms_mean": k_ms, "kernel_ms_min": float(np.min(kernel_ms)),
+                "algorithmic_bytes_per_launch": local_bytes,
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    # ---- e2e: public API, x from pinned host memory, y back to the host ----
+    x_host = (x_shard if N > 1 else x_full).cpu().pin_memory()
+    y_host = torch.empty(r1 - r0, dtype=torch.float32).pin_memory()
+    x_in = x_shard if N > 1 else x_full
+
+    def e2e_step():
+        x_in.copy_(x_host, non_blocking=True)
+        if N > 1:
+            dist.all_gather_into_tensor(x_full, x_shard)
+        spmv.merge_path_flat(A, x_full, y, stream=stream, sync=False)
+        y_host.copy_(y, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if N > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": nnz / (e2e_s / args.steps), "unit": UNIT,
+           "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(y_host.numel() * 4),
+           "ms_per_step": e2e_s / args.steps * 1e3,
+           "note": "matrix resident in HBM (as in the reference API, whose csr_t is device-resident); "
+                   "x uploaded and y downloaded every step, wall clock with a final synchronize"}
+
+    # correctness guard on the timed configuration (exact inputs -> exact sums)
+    chk = float(y.double().sum().item())
+
+    cpu = None
+    if rank == 0 and N == 1 and not args.no_cpu_baseline:
+        o, i_, v, xx = off.cpu().numpy(), idx.cpu().numpy(), val.cpu().numpy(), x_full.cpu().numpy()
+        sec, kind, y_cpu = cpu_spmv_seconds(o, i_, v, xx, rows, cols, 5, 1)
+        cpu = {"value": nnz / sec, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": "the full 2^20 x 2^25 workload, best of 5 passes of reference::spmv as shipped "
+                         "(single thread, includes its internal host copies)",
+               "host_cores_available": os.cpu_count(),
+               "y_matches_gpu_bit_exact": bool(np.array_equal(y_cpu, y.cpu().numpy()))}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(N), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(info.launches_per_spmv) * args.steps,
+            "clocks": clocks.report(),
+            "plan": {"grid_blocks": info.grid_blocks, "cta_threads": info.cta_threads,
+                     "smem_bytes": info.smem_bytes, "merge_tiles": int(info.num_merge_tiles)},
+            "y_checksum": chk,
+        }
+        print(json.dumps(line), flush=True)
+    if N > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -117,6 +117,17 @@ int loopsb_plan_info(const loopsb_plan_t* plan, loopsb_plan_info_t* info);
 int loopsb_plan_merge_coords_host(const loopsb_plan_t* plan, int32_t* host_xy,
                                   int64_t capacity_pairs);
 
+/* Kernel-time probes (measurement aid, off by default). After
+ * loopsb_plan_probe_begin(plan, capacity) every loopsb_spmv_f32 call on this
+ * plan brackets its DOMINANT kernel (the merge-path kernel, or the single
+ * kernel of the other schedules) with a cudaEvent pair recorded on the call's
+ * stream. loopsb_plan_probe_collect synchronises, writes up to `capacity`
+ * per-launch durations in milliseconds to a HOST array, returns the count in
+ * *n and switches the probes off again. */
+int loopsb_plan_probe_begin(loopsb_plan_t* plan, int32_t capacity);
+int loopsb_plan_probe_collect(loopsb_plan_t* plan, float* host_ms,
+                              int32_t capacity, int32_t* n);
+
 /* ---------------------------------------------------------------------------
  * SpMV  y = A * x, fp32 values, int32 ids. Replaces the host entry points
  *   algorithms::spmv::merge_path_flat   merge_path_flat.cuh:96-139

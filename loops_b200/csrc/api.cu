@@ -86,7 +86,42 @@ struct loopsb_plan {
   long long workspace_bytes = 0;
   // bcsr tensor-core path
   bcsr_tc::plan_data* tc = nullptr;
+  // kernel-time probes (loopsb_plan_probe_*)
+  cudaEvent_t* probe_ev = nullptr;  // 2 * probe_cap events
+  int probe_cap = 0;
+  int probe_n = 0;
+  bool probing = false;
 };
+
+namespace {
+// Brackets the dominant kernel of one SpMV call with an event pair.
+struct probe_scope {
+  loopsb_plan* p;
+  cudaStream_t s;
+  bool on;
+  probe_scope(loopsb_plan* plan, cudaStream_t stream)
+      : p(plan), s(stream), on(plan->probing && plan->probe_n < plan->probe_cap) {
+    if (on) cudaEventRecord(p->probe_ev[2 * p->probe_n], s);
+  }
+  void close() {
+    if (on) {
+      cudaEventRecord(p->probe_ev[2 * p->probe_n + 1], s);
+      p->probe_n++;
+      on = false;
+    }
+  }
+};
+void free_probes(loopsb_plan* p) {
+  if (p->probe_ev) {
+    for (int i = 0; i < 2 * p->probe_cap; ++i)
+      if (p->probe_ev[i]) cudaEventDestroy(p->probe_ev[i]);
+    delete[] p->probe_ev;
+  }
+  p->probe_ev = nullptr;
+  p->probe_cap = p->probe_n = 0;
+  p->probing = false;
+}
+}  // namespace
 
 extern "C" {
 
@@ -132,6 +167,7 @@ int loopsb_plan_destroy(loopsb_plan_t* plan) {
   if (plan->carry_row) cudaFree(plan->carry_row);
   if (plan->carry_val) cudaFree(plan->carry_val);
   if (plan->tc) bcsr_tc::destroy(plan->tc);
+  free_probes(plan);
   delete plan;
   return LOOPSB_OK;
 }
@@ -276,6 +312,33 @@ int loopsb_plan_merge_coords_host(const loopsb_plan_t* plan, int32_t* host_xy,
   return LOOPSB_OK;
 }
 
+int loopsb_plan_probe_begin(loopsb_plan_t* plan, int32_t capacity) {
+  LOOPSB_REQUIRE(plan != nullptr && capacity > 0 && capacity <= (1 << 20), "bad probe request");
+  free_probes(plan);
+  plan->probe_ev = new (std::nothrow) cudaEvent_t[2 * size_t(capacity)]();
+  if (!plan->probe_ev) { set_error("host allocation failed"); return LOOPSB_ERR_ALLOC; }
+  plan->probe_cap = capacity;
+  for (int i = 0; i < 2 * capacity; ++i)
+    LOOPSB_CUDA_TRY(cudaEventCreate(&plan->probe_ev[i]));
+  plan->probing = true;
+  return LOOPSB_OK;
+}
+
+int loopsb_plan_probe_collect(loopsb_plan_t* plan, float* host_ms,
+                              int32_t capacity, int32_t* n) {
+  LOOPSB_REQUIRE(plan != nullptr && host_ms != nullptr && n != nullptr, "null argument");
+  *n = 0;
+  plan->probing = false;
+  int count = plan->probe_n < capacity ? plan->probe_n : capacity;
+  for (int i = 0; i < count; ++i) {
+    LOOPSB_CUDA_TRY(cudaEventSynchronize(plan->probe_ev[2 * i + 1]));
+    LOOPSB_CUDA_TRY(cudaEventElapsedTime(&host_ms[i], plan->probe_ev[2 * i], plan->probe_ev[2 * i + 1]));
+  }
+  *n = count;
+  free_probes(plan);
+  return LOOPSB_OK;
+}
+
 int loopsb_spmv_f32(loopsb_plan_t* plan, const float* values,
                     const int32_t* col_indices, const int32_t* row_indices,
                     const float* x, float* y, int32_t num_rows,
@@ -297,6 +360,7 @@ int loopsb_spmv_f32(loopsb_plan_t* plan, const float* values,
     case LOOPSB_SCHED_MERGE_PATH_FLAT: {
       LOOPSB_REQUIRE(T == num_rows, "layout tiles must equal num_rows");
       const int nct = plan->num_cta_tiles;
+      probe_scope probe(plan, s);
       if (lay.kind == LOOPSB_LAYOUT_CSR) {
         mp::spmv_merge_kernel<kMergeThreads, kMergeTile, kMergeStages, true>
             <<<plan->grid, kMergeThreads, plan->smem_bytes, s>>>(
@@ -308,6 +372,7 @@ int loopsb_spmv_f32(loopsb_plan_t* plan, const float* values,
                 nullptr, lay.pitch, col_indices, values, x, y, plan->coords,
                 int(plan->M), kMergeG, T, A, nct, plan->carry_row, plan->carry_val);
       }
+      probe.close();
       LOOPSB_CUDA_TRY(cudaGetLastError());
       mp::spmv_merge_fixup_kernel<<<(nct + 255) / 256, 256, 0, s>>>(
           plan->carry_row, plan->carry_val, nct, T, y);
@@ -315,13 +380,16 @@ int loopsb_spmv_f32(loopsb_plan_t* plan, const float* values,
       return LOOPSB_OK;
     }
     case LOOPSB_SCHED_THREAD_MAPPED: {
+      if (lay.kind == LOOPSB_LAYOUT_COO) {
+        LOOPSB_REQUIRE(row_indices != nullptr, "COO needs row_indices");
+        LOOPSB_CUDA_TRY(cudaMemsetAsync(y, 0, size_t(num_rows) * sizeof(float), s));
+      }
+      probe_scope probe(plan, s);
       if (lay.kind == LOOPSB_LAYOUT_CSR) {
         LOOPSB_REQUIRE(T == num_rows, "layout tiles must equal num_rows");
         sk::spmv_thread_mapped_csr<<<plan->grid, 128, 0, s>>>(
             lay.offsets, col_indices, values, x, y, num_rows);
       } else if (lay.kind == LOOPSB_LAYOUT_COO) {
-        LOOPSB_REQUIRE(row_indices != nullptr, "COO needs row_indices");
-        LOOPSB_CUDA_TRY(cudaMemsetAsync(y, 0, size_t(num_rows) * sizeof(float), s));
         sk::spmv_coo_thread_mapped<<<(A + 127) / 128, 128, 0, s>>>(
             row_indices, col_indices, values, x, y, A);
       } else if (lay.kind == LOOPSB_LAYOUT_ELL) {
@@ -332,21 +400,26 @@ int loopsb_spmv_f32(loopsb_plan_t* plan, const float* values,
         set_error("use loopsb_spmv_bcsr_f32 / loopsb_spmv_bcsr4x4_bf16 for BCSR");
         return LOOPSB_ERR_UNSUPPORTED;
       }
+      probe.close();
       LOOPSB_CUDA_TRY(cudaGetLastError());
       return LOOPSB_OK;
     }
     case LOOPSB_SCHED_GROUP_MAPPED: {
       LOOPSB_REQUIRE(T == num_rows, "layout tiles must equal num_rows");
+      probe_scope probe(plan, s);
       sk::spmv_group_mapped_csr<<<plan->grid, sk::kGroupThreads, 0, s>>>(
           lay.offsets, col_indices, values, x, y, num_rows);
+      probe.close();
       LOOPSB_CUDA_TRY(cudaGetLastError());
       return LOOPSB_OK;
     }
     case LOOPSB_SCHED_WORK_ORIENTED: {
       LOOPSB_REQUIRE(T == num_rows, "layout tiles must equal num_rows");
       LOOPSB_CUDA_TRY(cudaMemsetAsync(y, 0, size_t(num_rows) * sizeof(float), s));
+      probe_scope probe(plan, s);
       sk::spmv_work_oriented_csr<<<plan->grid, sk::kWorkThreads, 0, s>>>(
           lay.offsets, col_indices, values, x, y, num_rows, A);
+      probe.close();
       LOOPSB_CUDA_TRY(cudaGetLastError());
       return LOOPSB_OK;
     }

@@ -35,6 +35,18 @@ class Plan:
                    "loopsb_plan_merge_coords_host")
         return out
 
+    def probe_begin(self, capacity: int):
+        """Bracket the dominant kernel of the next `capacity` SpMV calls with
+        CUDA events (recorded on each call's stream)."""
+        _lib.check(self._lib.loopsb_plan_probe_begin(self.handle, capacity), "loopsb_plan_probe_begin")
+
+    def probe_collect(self, capacity: int) -> np.ndarray:
+        ms = np.zeros(capacity, dtype=np.float32)
+        n = C.c_int32()
+        _lib.check(self._lib.loopsb_plan_probe_collect(self.handle, ms.ctypes.data, capacity, C.byref(n)),
+                   "loopsb_plan_probe_collect")
+        return ms[: n.value]
+
     def close(self):
         if getattr(self, "handle", None):
             self._lib.loopsb_plan_destroy(self.handle)
