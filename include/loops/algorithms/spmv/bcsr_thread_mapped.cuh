@@ -1,0 +1,4 @@
+/** @file bcsr_thread_mapped.cuh  algorithms::spmv::bcsr_thread_mapped is declared in loops/algorithms/spmv/spmv.cuh
+ *  (reference include/loops/algorithms/spmv/bcsr_thread_mapped.cuh). */
+#pragma once
+#include <loops/algorithms/spmv/spmv.cuh>

@@ -1,0 +1,127 @@
+/**
+ * @file spmv.cuh
+ * @brief `loops::algorithms::spmv::*` host entry points -- same names,
+ * argument lists and return types as the reference
+ * (include/loops/algorithms/spmv/{merge_path_flat,work_oriented,thread_mapped,
+ * group_mapped,coo_thread_mapped,ell_thread_mapped,ell_merge_path,
+ * bcsr_thread_mapped}.cuh), each a thin call into the C ABI of
+ * include/loopsb.h (libloopsb200.so) where the sm_100a kernels live.
+ *
+ * Like the reference wrappers they are synchronous (the stream is synchronised
+ * before returning); the ones that return `util::timer_t` time the SpMV
+ * launches only, excluding the per-matrix preprocess (reference
+ * merge_path_flat.cuh:111 precedes :121-122). Differences, both relaxations:
+ * `y` does not have to be zeroed by the caller, and failures surface as
+ * `error::exception_t` instead of being dropped.
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <loops/error.hxx>
+#include <loops/schedule.hxx>
+#include <loops/container/formats.hxx>
+#include <loops/container/vector.hxx>
+#include <loops/util/timer.hxx>
+#include <loops/algorithms/spmv/launch_box.hxx>
+#include <loopsb.h>
+
+namespace loops {
+namespace algorithms {
+namespace spmv {
+namespace detail {
+
+/// RAII handle of a loopsb plan (the reference's preprocess_t).
+struct plan_guard {
+  loopsb_plan_t* p = nullptr;
+  plan_guard(const loopsb_layout_t& lay, int schedule, cudaStream_t stream) {
+    error::throw_if_status(loopsb_plan_create(&p, &lay, schedule, stream), "loopsb_plan_create");
+  }
+  ~plan_guard() { loopsb_plan_destroy(p); }
+  plan_guard(const plan_guard&) = delete;
+  plan_guard& operator=(const plan_guard&) = delete;
+};
+
+template <typename vec_t>
+auto* raw(vec_t& v) { return thrust::raw_pointer_cast(v.data()); }
+
+inline util::timer_t run(const loopsb_layout_t& lay, int schedule, const float* values,
+                         const int* cols, const int* rows_idx, const float* x, float* y,
+                         std::size_t nrows, std::size_t ncols, cudaStream_t stream) {
+  plan_guard plan(lay, schedule, stream);
+  util::timer_t timer(stream);
+  timer.start();
+  error::throw_if_status(loopsb_spmv_f32(plan.p, values, cols, rows_idx, x, y,
+                                         static_cast<int32_t>(nrows), static_cast<int32_t>(ncols), stream),
+                         "loopsb_spmv_f32");
+  cudaStreamSynchronize(stream);
+  timer.stop();
+  return timer;
+}
+
+}  // namespace detail
+
+inline util::timer_t merge_path_flat(csr_t<int, int, float>& csr, vector_t<float>& x,
+                                     vector_t<float>& y, cudaStream_t stream = 0) {
+  return detail::run(csr.layout().descriptor(), LOOPSB_SCHED_MERGE_PATH_FLAT, detail::raw(csr.values),
+                     detail::raw(csr.indices), nullptr, detail::raw(x), detail::raw(y), csr.rows, csr.cols, stream);
+}
+
+inline void work_oriented(csr_t<int, int, float>& csr, vector_t<float>& x, vector_t<float>& y,
+                          cudaStream_t stream = 0) {
+  detail::run(csr.layout().descriptor(), LOOPSB_SCHED_WORK_ORIENTED, detail::raw(csr.values),
+              detail::raw(csr.indices), nullptr, detail::raw(x), detail::raw(y), csr.rows, csr.cols, stream);
+}
+
+inline void thread_mapped(csr_t<int, int, float>& csr, vector_t<float>& x, vector_t<float>& y,
+                          cudaStream_t stream = 0) {
+  detail::run(csr.layout().descriptor(), LOOPSB_SCHED_THREAD_MAPPED, detail::raw(csr.values),
+              detail::raw(csr.indices), nullptr, detail::raw(x), detail::raw(y), csr.rows, csr.cols, stream);
+}
+
+inline void group_mapped(csr_t<int, int, float>& csr, vector_t<float>& x, vector_t<float>& y,
+                         cudaStream_t stream = 0) {
+  detail::run(csr.layout().descriptor(), LOOPSB_SCHED_GROUP_MAPPED, detail::raw(csr.values),
+              detail::raw(csr.indices), nullptr, detail::raw(x), detail::raw(y), csr.rows, csr.cols, stream);
+}
+
+inline util::timer_t coo_thread_mapped(coo_t<int, float>& coo, vector_t<float>& x, vector_t<float>& y,
+                                       cudaStream_t stream = 0) {
+  layout::coo<int, int> lay(static_cast<int>(coo.nnzs));
+  return detail::run(lay.descriptor(), LOOPSB_SCHED_THREAD_MAPPED, detail::raw(coo.values),
+                     detail::raw(coo.col_indices), detail::raw(coo.row_indices), detail::raw(x),
+                     detail::raw(y), coo.rows, coo.cols, stream);
+}
+
+inline void ell_thread_mapped(ell_t<int, float>& ell, vector_t<float>& x, vector_t<float>& y,
+                              cudaStream_t stream = 0) {
+  detail::run(ell.layout().descriptor(), LOOPSB_SCHED_THREAD_MAPPED, detail::raw(ell.values),
+              detail::raw(ell.indices), nullptr, detail::raw(x), detail::raw(y), ell.rows, ell.cols, stream);
+}
+
+inline util::timer_t ell_merge_path(ell_t<int, float>& ell, vector_t<float>& x, vector_t<float>& y,
+                                    cudaStream_t stream = 0) {
+  return detail::run(ell.layout().descriptor(), LOOPSB_SCHED_MERGE_PATH_FLAT, detail::raw(ell.values),
+                     detail::raw(ell.indices), nullptr, detail::raw(x), detail::raw(y), ell.rows, ell.cols,
+                     stream);
+}
+
+template <std::size_t R, std::size_t C>
+util::timer_t bcsr_thread_mapped(bcsr_t<R, C, int, int, float>& bcsr, vector_t<float>& x,
+                                 vector_t<float>& y, cudaStream_t stream = 0) {
+  const loopsb_layout_t lay = bcsr.layout().descriptor();
+  util::timer_t timer(stream);
+  timer.start();
+  error::throw_if_status(
+      loopsb_spmv_bcsr_f32(int32_t(R), int32_t(C), &lay, detail::raw(bcsr.values),
+                           detail::raw(bcsr.block_col_indices), detail::raw(x), detail::raw(y),
+                           static_cast<int32_t>(bcsr.rows), stream),
+      "loopsb_spmv_bcsr_f32");
+  cudaStreamSynchronize(stream);
+  timer.stop();
+  return timer;
+}
+
+}  // namespace spmv
+}  // namespace algorithms
+}  // namespace loops

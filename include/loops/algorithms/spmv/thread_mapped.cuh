@@ -1,0 +1,4 @@
+/** @file thread_mapped.cuh  algorithms::spmv::thread_mapped is declared in loops/algorithms/spmv/spmv.cuh
+ *  (reference include/loops/algorithms/spmv/thread_mapped.cuh). */
+#pragma once
+#include <loops/algorithms/spmv/spmv.cuh>

@@ -1,0 +1,234 @@
+/**
+ * @file formats.hxx
+ * @brief Sparse containers. Same struct names, members, dtypes and padding
+ * rules as the reference (include/loops/container/{csr,coo,ell,bcsr}.hxx);
+ * they are the INPUT MEMORY FORMATS of the SpMV path. Conversions run on the
+ * host with std:: algorithms (set-up code, not the hot path).
+ */
+#pragma once
+
+#include <algorithm>
+#include <cstddef>
+#include <numeric>
+#include <vector>
+
+#include <loops/container/vector.hxx>
+#include <loops/container/layout.hxx>
+#include <loops/memory.hxx>
+
+namespace loops {
+using namespace memory;
+
+template <typename index_t, typename value_t, memory_space_t space = memory_space_t::device>
+struct coo_t;
+template <typename index_t, typename offset_t, typename value_t, memory_space_t space = memory_space_t::device>
+struct csr_t;
+
+/// COO: row_indices / col_indices / values, each nnzs long.
+template <typename index_t, typename value_t, memory_space_t space>
+struct coo_t {
+  std::size_t rows = 0, cols = 0, nnzs = 0;
+  vector_t<index_t, space> row_indices;
+  vector_t<index_t, space> col_indices;
+  vector_t<value_t, space> values;
+
+  coo_t() = default;
+  coo_t(std::size_t r, std::size_t c, std::size_t nnz)
+      : rows(r), cols(c), nnzs(nnz), row_indices(nnz), col_indices(nnz), values(nnz) {}
+
+  template <auto rhs_space>
+  coo_t(const coo_t<index_t, value_t, rhs_space>& rhs)
+      : rows(rhs.rows), cols(rhs.cols), nnzs(rhs.nnzs),
+        row_indices(rhs.row_indices), col_indices(rhs.col_indices), values(rhs.values) {}
+
+  /// Expand CSR row offsets into one row id per nonzero.
+  template <auto rhs_space, typename offset_t>
+  coo_t(const csr_t<index_t, offset_t, value_t, rhs_space>& csr);
+
+  /// Row-major (row, col) ordering; ties keep their input order.
+  void sort_by_row() {
+    thrust::host_vector<index_t> r(row_indices), c(col_indices);
+    thrust::host_vector<value_t> v(values);
+    std::vector<std::size_t> perm(nnzs);
+    std::iota(perm.begin(), perm.end(), std::size_t(0));
+    std::stable_sort(perm.begin(), perm.end(), [&](std::size_t a, std::size_t b) {
+      return r[a] != r[b] ? r[a] < r[b] : c[a] < c[b];
+    });
+    thrust::host_vector<index_t> r2(nnzs), c2(nnzs);
+    thrust::host_vector<value_t> v2(nnzs);
+    for (std::size_t i = 0; i < nnzs; ++i) {
+      r2[i] = r[perm[i]]; c2[i] = c[perm[i]]; v2[i] = v[perm[i]];
+    }
+    row_indices = r2; col_indices = c2; values = v2;
+  }
+};
+
+/// CSR: offsets[rows+1], indices[nnzs], values[nnzs].
+template <typename index_t, typename offset_t, typename value_t, memory_space_t space>
+struct csr_t {
+  std::size_t rows = 0, cols = 0, nnzs = 0;
+  vector_t<offset_t, space> offsets;
+  vector_t<index_t, space> indices;
+  vector_t<value_t, space> values;
+
+  csr_t() = default;
+  csr_t(std::size_t r, std::size_t c, std::size_t nnz)
+      : rows(r), cols(c), nnzs(nnz), offsets(r + 1), indices(nnz), values(nnz) {}
+
+  template <auto rhs_space>
+  csr_t(const csr_t<index_t, offset_t, value_t, rhs_space>& rhs)
+      : rows(rhs.rows), cols(rhs.cols), nnzs(rhs.nnzs),
+        offsets(rhs.offsets), indices(rhs.indices), values(rhs.values) {}
+
+  /// From COO: sort by (row, col), then count rows into offsets.
+  template <auto rhs_space>
+  csr_t(const coo_t<index_t, value_t, rhs_space>& coo)
+      : rows(coo.rows), cols(coo.cols), nnzs(coo.nnzs) {
+    coo_t<index_t, value_t, memory_space_t::host> sorted(coo);
+    sorted.sort_by_row();
+    thrust::host_vector<offset_t> off(rows + 1, offset_t(0));
+    for (std::size_t i = 0; i < nnzs; ++i)
+      off[sorted.row_indices[i] + 1] += 1;
+    for (std::size_t r = 0; r < rows; ++r)
+      off[r + 1] += off[r];
+    offsets = off;
+    indices = sorted.col_indices;
+    values = sorted.values;
+  }
+
+  layout::csr<index_t, offset_t> layout() const {
+    return layout::csr<index_t, offset_t>(
+        thrust::raw_pointer_cast(offsets.data()), static_cast<index_t>(rows),
+        static_cast<offset_t>(nnzs));
+  }
+};
+
+template <typename index_t, typename value_t, memory_space_t space>
+template <auto rhs_space, typename offset_t>
+coo_t<index_t, value_t, space>::coo_t(const csr_t<index_t, offset_t, value_t, rhs_space>& csr)
+    : rows(csr.rows), cols(csr.cols), nnzs(csr.nnzs), col_indices(csr.indices), values(csr.values) {
+  thrust::host_vector<offset_t> off(csr.offsets);
+  thrust::host_vector<index_t> r(nnzs);
+  for (std::size_t row = 0; row < rows; ++row)
+    for (offset_t k = off[row]; k < off[row + 1]; ++k)
+      r[k] = static_cast<index_t>(row);
+  row_indices = r;
+}
+
+/// ELL: row-major rows*pitch slabs; padding = column sentinel() (-1), value 0.
+template <typename index_t, typename value_t, memory_space_t space = memory_space_t::device>
+struct ell_t {
+  std::size_t rows = 0, cols = 0, nnzs = 0, pitch = 0;
+  vector_t<index_t, space> indices;
+  vector_t<value_t, space> values;
+
+  static __host__ __device__ index_t sentinel() { return static_cast<index_t>(-1); }
+
+  ell_t() = default;
+  ell_t(std::size_t r, std::size_t c, std::size_t nnz, std::size_t p)
+      : rows(r), cols(c), nnzs(nnz), pitch(p), indices(r * p, sentinel()), values(r * p, value_t(0)) {}
+
+  template <auto rhs_space>
+  ell_t(const ell_t<index_t, value_t, rhs_space>& rhs)
+      : rows(rhs.rows), cols(rhs.cols), nnzs(rhs.nnzs), pitch(rhs.pitch),
+        indices(rhs.indices), values(rhs.values) {}
+
+  template <typename offset_t, auto rhs_space>
+  static std::size_t max_nnz_per_row(const csr_t<index_t, offset_t, value_t, rhs_space>& csr) {
+    thrust::host_vector<offset_t> off(csr.offsets);
+    std::size_t widest = 0;
+    for (std::size_t r = 0; r < csr.rows; ++r)
+      widest = std::max(widest, static_cast<std::size_t>(off[r + 1] - off[r]));
+    return widest;
+  }
+
+  /// pitch = widest row; row r's k-th stored entry lands in slot r*pitch + k.
+  template <typename offset_t, auto rhs_space>
+  ell_t(const csr_t<index_t, offset_t, value_t, rhs_space>& csr)
+      : rows(csr.rows), cols(csr.cols), nnzs(csr.nnzs), pitch(max_nnz_per_row(csr)) {
+    thrust::host_vector<offset_t> off(csr.offsets);
+    thrust::host_vector<index_t> idx(csr.indices);
+    thrust::host_vector<value_t> val(csr.values);
+    thrust::host_vector<index_t> e_idx(rows * pitch, sentinel());
+    thrust::host_vector<value_t> e_val(rows * pitch, value_t(0));
+    for (std::size_t r = 0; r < rows; ++r) {
+      std::size_t slot = r * pitch;
+      for (offset_t k = off[r]; k < off[r + 1]; ++k, ++slot) {
+        e_idx[slot] = idx[k];
+        e_val[slot] = val[k];
+      }
+    }
+    indices = e_idx;
+    values = e_val;
+  }
+
+  layout::ell<index_t, index_t> layout() const {
+    return layout::ell<index_t, index_t>(static_cast<index_t>(rows), static_cast<index_t>(pitch));
+  }
+};
+
+/// BCSR: R x C dense blocks, values[b*R*C + i*C + j]; block columns ascending
+/// inside a block-row; CSR entries are assigned into their block, padding 0.
+template <std::size_t R, std::size_t C, typename index_t, typename offset_t, typename value_t,
+          memory_space_t space = memory_space_t::device>
+struct bcsr_t {
+  static_assert(R > 0 && C > 0, "BCSR block dims must be positive.");
+  static constexpr std::size_t kBlockRows = R, kBlockCols = C, kBlockSize = R * C;
+
+  std::size_t rows = 0, cols = 0, nnzs = 0;
+  std::size_t num_block_rows = 0, num_block_cols = 0, num_blocks = 0;
+  vector_t<offset_t, space> block_offsets;
+  vector_t<index_t, space> block_col_indices;
+  vector_t<value_t, space> values;
+
+  bcsr_t() = default;
+
+  template <auto rhs_space>
+  bcsr_t(const bcsr_t<R, C, index_t, offset_t, value_t, rhs_space>& rhs)
+      : rows(rhs.rows), cols(rhs.cols), nnzs(rhs.nnzs), num_block_rows(rhs.num_block_rows),
+        num_block_cols(rhs.num_block_cols), num_blocks(rhs.num_blocks),
+        block_offsets(rhs.block_offsets), block_col_indices(rhs.block_col_indices), values(rhs.values) {}
+
+  template <auto rhs_space, typename csr_offset_t>
+  bcsr_t(const csr_t<index_t, csr_offset_t, value_t, rhs_space>& csr)
+      : rows(csr.rows), cols(csr.cols), nnzs(csr.nnzs),
+        num_block_rows((csr.rows + R - 1) / R), num_block_cols((csr.cols + C - 1) / C) {
+    thrust::host_vector<csr_offset_t> off(csr.offsets);
+    thrust::host_vector<index_t> idx(csr.indices);
+    thrust::host_vector<value_t> val(csr.values);
+    std::vector<offset_t> b_off(num_block_rows + 1, offset_t(0));
+    std::vector<index_t> b_col;
+    std::vector<value_t> b_val;
+    std::vector<index_t> seen;  // block columns touched by the current block-row
+    for (std::size_t br = 0; br < num_block_rows; ++br) {
+      const std::size_t lo = br * R, hi = std::min(lo + R, rows);
+      seen.clear();
+      for (csr_offset_t a = off[lo]; a < off[hi]; ++a)
+        seen.push_back(static_cast<index_t>(idx[a] / C));
+      std::sort(seen.begin(), seen.end());
+      seen.erase(std::unique(seen.begin(), seen.end()), seen.end());
+      const std::size_t first_block = b_col.size();
+      b_col.insert(b_col.end(), seen.begin(), seen.end());
+      b_val.resize(b_val.size() + seen.size() * kBlockSize, value_t(0));
+      for (std::size_t r = lo; r < hi; ++r)
+        for (csr_offset_t a = off[r]; a < off[r + 1]; ++a) {
+          const index_t bc = static_cast<index_t>(idx[a] / C);
+          const std::size_t local = std::lower_bound(seen.begin(), seen.end(), bc) - seen.begin();
+          b_val[(first_block + local) * kBlockSize + (r - lo) * C + (idx[a] % C)] = val[a];
+        }
+      b_off[br + 1] = static_cast<offset_t>(b_col.size());
+    }
+    num_blocks = b_col.size();
+    block_offsets = thrust::host_vector<offset_t>(b_off.begin(), b_off.end());
+    block_col_indices = thrust::host_vector<index_t>(b_col.begin(), b_col.end());
+    values = thrust::host_vector<value_t>(b_val.begin(), b_val.end());
+  }
+
+  layout::bcsr<index_t, offset_t> layout() const {
+    return layout::bcsr<index_t, offset_t>(
+        thrust::raw_pointer_cast(block_offsets.data()), static_cast<index_t>(num_block_rows),
+        static_cast<offset_t>(num_blocks));
+  }
+};
+
+}  // namespace loops
