@@ -302,7 +302,7 @@ def main():
     k_ms = float(np.mean(kernel_ms))
     achieved = local_bytes / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "spmv_merge_kernel<256,4096,2,true>",
+                "traffic": None, "peak_source": peak_src, "kernel": f"spmv_merge_kernel (CTA {info.cta_threads} thr, grid {info.grid_blocks}, smem {info.smem_bytes} B)",
                 "kernel_ms_mean": k_ms, "kernel_ms_min": float(np.min(kernel_ms)),
                 "algorithmic_bytes_per_launch": local_bytes,
                 "frac_of_nominal_8TBs": achieved / 8000.0}

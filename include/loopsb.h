@@ -125,6 +125,13 @@ int loopsb_plan_merge_coords_host(const loopsb_plan_t* plan, int32_t* host_xy,
  * per-launch durations in milliseconds to a HOST array, returns the count in
  * *n and switches the probes off again. */
 int loopsb_plan_probe_begin(loopsb_plan_t* plan, int32_t capacity);
+/* Tuning aid: when the environment variable LOOPSB_DEBUG_PHASES is set at plan
+ * creation, the merge-path kernel accumulates, per CTA (thread 0), the SM
+ * cycles spent in {stage wait, gather, walk, scan, store, refill} and the
+ * number of tiles; this copies the last launch's 8 x int64 per CTA to the host
+ * (grid_blocks CTAs). LOOPSB_ERR_UNSUPPORTED when the counters are off. */
+int loopsb_plan_debug_phases_host(const loopsb_plan_t* plan, int64_t* host_out,
+                                  int64_t capacity_ctas);
 int loopsb_plan_probe_collect(loopsb_plan_t* plan, float* host_ms,
                               int32_t capacity, int32_t* n);
 

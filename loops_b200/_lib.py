@@ -71,6 +71,7 @@ SIGNATURES = {
     "loopsb_plan_destroy": (C.c_int, [_P]),
     "loopsb_plan_info": (C.c_int, [_P, C.POINTER(PlanInfo)]),
     "loopsb_plan_merge_coords_host": (C.c_int, [_P, _P, C.c_int64]),
+    "loopsb_plan_debug_phases_host": (C.c_int, [_P, _P, C.c_int64]),
     "loopsb_plan_probe_begin": (C.c_int, [_P, C.c_int32]),
     "loopsb_plan_probe_collect": (C.c_int, [_P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "loopsb_spmv_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P]),

@@ -8,6 +8,7 @@
 #include "bcsr_tc.cuh"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <mutex>
 #include <new>
 
@@ -56,15 +57,81 @@ const device_props* current_device() {
 
 using namespace loopsb;
 
-// Merge-path SpMV geometry: 256-thread CTAs, 4 reference merge tiles (4096
-// items) per CTA tile, double-buffered stage, 2 CTAs per SM.
+// Merge-path SpMV geometry variants: {CTA threads, merge tiles per CTA tile,
+// stages, target CTAs/SM}. Variant 0 is the default; LOOPSB_MERGE_VARIANT
+// selects another one at plan creation (tuning aid).
 namespace {
-constexpr int kMergeThreads = 256;
-constexpr int kMergeG = 4;
-constexpr int kMergeTile = kMergeG * mp::kRefItemsPerMergeTile;
-constexpr int kMergeStages = 2;
-constexpr int kMergeCtasPerSm = 2;
-using merge_shared_t = mp::merge_shared<kMergeThreads, kMergeTile, kMergeStages>;
+struct merge_variant {
+  int threads, g, stages, ctas_per_sm, smem;
+  int carveout_kb;  // preferred shared-memory carve-out per SM (keeps the L1 that tracks gather misses)
+  void (*launch)(bool array_ends, int grid, int smem, cudaStream_t s, const int* row_end, int pitch,
+                 const int* indices, const float* values, const float* x, float* y, const int2* coords,
+                 int M, int T, int A, int nct, int* carry_row, float* carry_val, long long* phases);
+  cudaError_t (*prepare)(int smem);
+};
+
+template <int THREADS, int G, int STAGES, int MINB>
+struct merge_inst {
+  static constexpr int TILE = G * mp::kRefItemsPerMergeTile;
+  using shared_t = mp::merge_shared<THREADS, TILE, STAGES>;
+  static void launch(bool array_ends, int grid, int smem, cudaStream_t s, const int* row_end, int pitch,
+                     const int* indices, const float* values, const float* x, float* y, const int2* coords,
+                     int M, int T, int A, int nct, int* carry_row, float* carry_val, long long* phases) {
+    if (array_ends)
+      mp::spmv_merge_kernel<THREADS, TILE, STAGES, MINB, true><<<grid, THREADS, smem, s>>>(
+          row_end, pitch, indices, values, x, y, coords, M, G, T, A, nct, carry_row, carry_val, phases);
+    else
+      mp::spmv_merge_kernel<THREADS, TILE, STAGES, MINB, false><<<grid, THREADS, smem, s>>>(
+          row_end, pitch, indices, values, x, y, coords, M, G, T, A, nct, carry_row, carry_val, phases);
+  }
+  // Smallest carve-out bucket (KB) that holds MINB CTAs (+1 KB driver reserve each).
+  static constexpr int carveout_kb() {
+    const int need = (MINB * (int(sizeof(shared_t)) + 1024) + 1023) / 1024;
+    const int buckets[] = {8, 16, 32, 64, 100, 132, 164, 196, 228};
+    for (int b : buckets) if (need <= b) return b;
+    return 228;
+  }
+  static cudaError_t prepare(int smem) {
+    auto ka = mp::spmv_merge_kernel<THREADS, TILE, STAGES, MINB, true>;
+    auto kp = mp::spmv_merge_kernel<THREADS, TILE, STAGES, MINB, false>;
+    const int pct = (carveout_kb() * 100 + 227) / 228;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ka, cudaFuncAttributePreferredSharedMemoryCarveout, pct)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kp, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  }
+  static constexpr merge_variant variant() {
+    return merge_variant{THREADS, G, STAGES, MINB, int(sizeof(shared_t)), carveout_kb(), &launch, &prepare};
+  }
+};
+
+const merge_variant kMergeVariants[] = {
+    merge_inst<256, 4, 2, 2>::variant(),  // 0: 256 thr, 4096 items, 2 stages, 2 CTAs/SM
+    merge_inst<128, 2, 2, 5>::variant(),  // 1: 128 thr, 2048 items, 2 stages, 5 CTAs/SM
+    merge_inst<128, 2, 3, 4>::variant(),  // 2: 128 thr, 2048 items, 3 stages, 4 CTAs/SM
+    merge_inst<256, 2, 2, 5>::variant(),  // 3: 256 thr, 2048 items (8/thread), 5 CTAs/SM
+    merge_inst<512, 4, 2, 2>::variant(),  // 4: 512 thr, 4096 items (8/thread), 2 CTAs/SM
+    merge_inst<128, 1, 3, 8>::variant(),  // 5: 128 thr, 1024 items (8/thread), 8 CTAs/SM
+    merge_inst<256, 4, 3, 1>::variant(),  // 6: 256 thr, 4096 items, 3 stages, 1 CTA/SM
+    merge_inst<256, 2, 2, 3>::variant(),  // 7: 256 thr, 2048 items, 2 stages, 3 CTAs/SM (132 KB)
+    merge_inst<256, 2, 2, 4>::variant(),  // 8: 256 thr, 2048 items, 2 stages, 4 CTAs/SM (196 KB)
+    merge_inst<128, 1, 2, 6>::variant(),  // 9: 128 thr, 1024 items, 2 stages, 6 CTAs/SM (132 KB)
+    merge_inst<128, 2, 2, 3>::variant(),  // 10: 128 thr, 2048 items, 2 stages, 3 CTAs/SM (132 KB)
+    merge_inst<128, 1, 2, 7>::variant(),  // 11: 128 thr, 1024 items, 2 stages, 7 CTAs/SM (164 KB)
+    merge_inst<256, 1, 2, 6>::variant(),  // 12: 256 thr, 1024 items (4/thread), 6 CTAs/SM
+};
+constexpr int kNumMergeVariants = int(sizeof(kMergeVariants) / sizeof(kMergeVariants[0]));
+
+int merge_variant_from_env() {
+  // Default: 128-thread CTAs over one 1024-item merge tile each, 6 CTAs/SM
+  // inside the 132 KB carve-out (measured best on B200, profiles/).
+  constexpr int kDefault = 9;
+  const char* e = getenv("LOOPSB_MERGE_VARIANT");
+  if (!e) return kDefault;
+  int v = atoi(e);
+  return (v >= 0 && v < kNumMergeVariants) ? v : kDefault;
+}
 }  // namespace
 
 struct loopsb_plan {
@@ -76,6 +143,8 @@ struct loopsb_plan {
   int2* coords = nullptr;     // S(b*1024), b = 0..M
   long long M = 0;
   int num_cta_tiles = 0;
+  int variant = 0;
+  long long* phases = nullptr;  // LOOPSB_DEBUG_PHASES=1: per-CTA phase cycle counters
   int* carry_row = nullptr;
   float* carry_val = nullptr;
   // launch geometry of the SpMV kernel
@@ -166,6 +235,7 @@ int loopsb_plan_destroy(loopsb_plan_t* plan) {
   if (plan->coords) cudaFree(plan->coords);
   if (plan->carry_row) cudaFree(plan->carry_row);
   if (plan->carry_val) cudaFree(plan->carry_val);
+  if (plan->phases) cudaFree(plan->phases);
   if (plan->tc) bcsr_tc::destroy(plan->tc);
   free_probes(plan);
   delete plan;
@@ -208,11 +278,13 @@ int loopsb_plan_create(loopsb_plan_t** out, const loopsb_layout_t* lay,
     }
     const long long W = (long long)T + A;
     p->M = (W + mp::kRefItemsPerMergeTile - 1) / mp::kRefItemsPerMergeTile;
-    p->num_cta_tiles = int((p->M + kMergeG - 1) / kMergeG);
-    p->cta_threads = kMergeThreads;
-    p->smem_bytes = int(sizeof(merge_shared_t));
+    p->variant = merge_variant_from_env();
+    const merge_variant& mv = kMergeVariants[p->variant];
+    p->num_cta_tiles = int((p->M + mv.g - 1) / mv.g);
+    p->cta_threads = mv.threads;
+    p->smem_bytes = mv.smem;
     p->launches = 2;
-    int grid = kMergeCtasPerSm * dp->sm_count;
+    int grid = mv.ctas_per_sm * dp->sm_count;
     if (grid > p->num_cta_tiles) grid = p->num_cta_tiles;
     p->grid = grid;
     if (p->M > 0) {
@@ -238,10 +310,15 @@ int loopsb_plan_create(loopsb_plan_t** out, const loopsb_layout_t* lay,
         set_error("merge_coords_kernel launch failed");
         return fail(LOOPSB_ERR_CUDA);
       }
-      auto kern_a = mp::spmv_merge_kernel<kMergeThreads, kMergeTile, kMergeStages, true>;
-      auto kern_p = mp::spmv_merge_kernel<kMergeThreads, kMergeTile, kMergeStages, false>;
-      if (cudaFuncSetAttribute(kern_a, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes) != cudaSuccess ||
-          cudaFuncSetAttribute(kern_p, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes) != cudaSuccess) {
+      if (getenv("LOOPSB_DEBUG_PHASES")) {
+        if (cudaMalloc(&p->phases, size_t(p->grid) * 8 * sizeof(long long)) != cudaSuccess) {
+          (void)cudaGetLastError();
+          p->phases = nullptr;
+        } else {
+          cudaMemsetAsync(p->phases, 0, size_t(p->grid) * 8 * sizeof(long long), s);
+        }
+      }
+      if (mv.prepare(p->smem_bytes) != cudaSuccess) {
         set_error("cannot opt in to %d bytes of dynamic shared memory", p->smem_bytes);
         (void)cudaGetLastError();
         return fail(LOOPSB_ERR_CUDA);
@@ -312,6 +389,16 @@ int loopsb_plan_merge_coords_host(const loopsb_plan_t* plan, int32_t* host_xy,
   return LOOPSB_OK;
 }
 
+int loopsb_plan_debug_phases_host(const loopsb_plan_t* plan, int64_t* host_out,
+                                  int64_t capacity_ctas) {
+  LOOPSB_REQUIRE(plan != nullptr && host_out != nullptr, "null argument");
+  if (!plan->phases) { set_error("phase counters are off (set LOOPSB_DEBUG_PHASES=1 before creating the plan)"); return LOOPSB_ERR_UNSUPPORTED; }
+  LOOPSB_REQUIRE(capacity_ctas >= plan->grid, "host buffer too small");
+  LOOPSB_CUDA_TRY(cudaDeviceSynchronize());
+  LOOPSB_CUDA_TRY(cudaMemcpy(host_out, plan->phases, size_t(plan->grid) * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return LOOPSB_OK;
+}
+
 int loopsb_plan_probe_begin(loopsb_plan_t* plan, int32_t capacity) {
   LOOPSB_REQUIRE(plan != nullptr && capacity > 0 && capacity <= (1 << 20), "bad probe request");
   free_probes(plan);
@@ -361,17 +448,11 @@ int loopsb_spmv_f32(loopsb_plan_t* plan, const float* values,
       LOOPSB_REQUIRE(T == num_rows, "layout tiles must equal num_rows");
       const int nct = plan->num_cta_tiles;
       probe_scope probe(plan, s);
-      if (lay.kind == LOOPSB_LAYOUT_CSR) {
-        mp::spmv_merge_kernel<kMergeThreads, kMergeTile, kMergeStages, true>
-            <<<plan->grid, kMergeThreads, plan->smem_bytes, s>>>(
-                lay.offsets + 1, 0, col_indices, values, x, y, plan->coords,
-                int(plan->M), kMergeG, T, A, nct, plan->carry_row, plan->carry_val);
-      } else {
-        mp::spmv_merge_kernel<kMergeThreads, kMergeTile, kMergeStages, false>
-            <<<plan->grid, kMergeThreads, plan->smem_bytes, s>>>(
-                nullptr, lay.pitch, col_indices, values, x, y, plan->coords,
-                int(plan->M), kMergeG, T, A, nct, plan->carry_row, plan->carry_val);
-      }
+      const merge_variant& mv = kMergeVariants[plan->variant];
+      const bool array_ends = lay.kind == LOOPSB_LAYOUT_CSR;
+      mv.launch(array_ends, plan->grid, plan->smem_bytes, s, array_ends ? lay.offsets + 1 : nullptr,
+                lay.pitch, col_indices, values, x, y, plan->coords, int(plan->M), T, A, nct,
+                plan->carry_row, plan->carry_val, plan->phases);
       probe.close();
       LOOPSB_CUDA_TRY(cudaGetLastError());
       mp::spmv_merge_fixup_kernel<<<(nct + 255) / 256, 256, 0, s>>>(

@@ -49,7 +49,7 @@ struct tile_meta {
 template <int THREADS, int TILE, int STAGES>
 struct merge_shared {
   static constexpr int kStageInts = 2 * TILE + 32;
-  static constexpr int kProdWords = TILE + TILE / 32 + 8;
+  static constexpr int kProdWords = TILE + TILE / 32 + 20;  // + speculative reads past na
   alignas(16) int stage[STAGES][kStageInts];
   alignas(16) float prod[kProdWords];
   unsigned long long full[STAGES];
@@ -131,15 +131,16 @@ __device__ __forceinline__ void issue_tile(
 // ELL (ARRAY_ENDS == false): padding slots carry column -1 and contribute 0
 // (reference ell_merge_path.cuh:60).
 // ---------------------------------------------------------------------------
-template <int THREADS, int TILE, int STAGES, bool ARRAY_ENDS>
-__global__ void __launch_bounds__(THREADS, 2)
+template <int THREADS, int TILE, int STAGES, int MINB, bool ARRAY_ENDS>
+__global__ void __launch_bounds__(THREADS, MINB)
     spmv_merge_kernel(const int* __restrict__ row_end, int pitch,
                       const int* __restrict__ indices,
                       const float* __restrict__ values,
                       const float* __restrict__ x, float* __restrict__ y,
                       const int2* __restrict__ coords, int M, int G, int T,
                       int A, int num_cta_tiles, int* __restrict__ carry_row,
-                      float* __restrict__ carry_val) {
+                      float* __restrict__ carry_val,
+                      long long* __restrict__ phase_cycles) {
   using shared_t = merge_shared<THREADS, TILE, STAGES>;
   constexpr int IPT = TILE / THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -181,11 +182,21 @@ __global__ void __launch_bounds__(THREADS, 2)
   }
   __syncthreads();
 
+  // Optional per-phase cycle accounting (thread 0 of every CTA; tuning aid).
+  long long ph[6] = {0, 0, 0, 0, 0, 0};
+  long long tick = 0;
+  const bool timing = (phase_cycles != nullptr) && (t == 0);
+  auto lap = [&](int which) {
+    if (timing) { const long long now = clock64(); ph[which] += now - tick; tick = now; }
+  };
+  if (timing) tick = clock64();
+
   int k = 0;
   for (int j = first_tile; j < num_cta_tiles; j += stride, ++k) {
     const int st = k % STAGES;
     const uint32_t parity = uint32_t(k / STAGES) & 1u;
     loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.full[st]), parity);
+    lap(0);  // waiting for the stage
 
     const tile_meta m = sm.meta[st];
     int* sidx = &sm.stage[st][0];
@@ -198,8 +209,8 @@ __global__ void __launch_bounds__(THREADS, 2)
                         (m.bulk_v < m.skew_v + m.na) ||
                         (ARRAY_ENDS && m.bulk_r < m.skew_r + m.nt);
     if (ragged) {
-      for (int r = m.bulk_i + t; r < m.skew_i + m.na; r += THREADS)
-        sidx[r] = indices[m.sy + (r - m.skew_i)];
+      for (int r = m.bulk_i + t; r < ((m.skew_i + m.na + 3) & ~3); r += THREADS)
+        sidx[r] = (r < m.skew_i + m.na) ? indices[m.sy + (r - m.skew_i)] : 0;
       for (int r = m.bulk_v + t; r < m.skew_v + m.na; r += THREADS)
         sval[r] = values[m.sy + (r - m.skew_v)];
       if (ARRAY_ENDS)
@@ -208,51 +219,89 @@ __global__ void __launch_bounds__(THREADS, 2)
       __syncthreads();
     }
 
+    // Row end of tile-local row i, relative to the tile's first atom.
+    auto rel_end = [&](int i) -> int {
+      if (ARRAY_ENDS) return sre[m.skew_r + i] - m.sy;
+      return (m.sx + i + 1) * pitch - m.sy;
+    };
+    const int items = m.nt + m.na;
+    int d = t * IPT;
+    if (d > items) d = items;
+    int row, atom0;
+    // Per-thread diagonal search on the staged row-end window. Independent of
+    // the x gathers, so it is placed between their issue and their use and
+    // runs while they are in flight.
+    auto thread_search = [&]() {
+      int lo = d - m.na; if (lo < 0) lo = 0;
+      int hi = d < m.nt ? d : m.nt;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (rel_end(mid) <= d - mid - 1) lo = mid + 1; else hi = mid;
+      }
+      row = lo;
+      atom0 = d - lo;
+    };
+
     // ---------------- gather / multiply ----------------
     if (m.skew_i == m.skew_v) {
       const int skew = m.skew_i;
-      const int nchunks = (skew + m.na + 3) >> 2;
+      const int nchunks = m.na > 0 ? (skew + m.na + 3) >> 2 : 0;
       const int4* sidx4 = reinterpret_cast<const int4*>(sidx);
       const float4* sval4 = reinterpret_cast<const float4*>(sval);
-      constexpr int U = 4;
-      for (int base = 0; base < nchunks; base += THREADS * U) {
-        int4 ci[U];
-        float4 cv[U];
-        float xv[U][4];
+      constexpr int U = TILE / (4 * THREADS);   // 16-byte chunks per thread
+      const unsigned una = unsigned(m.na);
+      int4 ci[U];
+      float4 cv[U];
+      float xv[U][4];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int c = u * THREADS + t;
+        // chunks past the end read chunk 0 and are masked at the store; every
+        // index inside a present chunk is a real column id (neighbouring
+        // atoms) or was sanitised above.
+        const int cc = (c < nchunks) ? c : 0;
+        ci[u] = sidx4[cc];
+        cv[u] = sval4[cc];
+      }
+      if (nchunks > 0) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int c = base + u * THREADS + t;
-          if (c < nchunks) {
-            ci[u] = sidx4[c];
-            cv[u] = sval4[c];
-          } else {
-            ci[u] = make_int4(0, 0, 0, 0);
-            cv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int c = base + u * THREADS + t;
-          const int p0 = 4 * c - skew;
           const int cols[4] = {ci[u].x, ci[u].y, ci[u].z, ci[u].w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int p = p0 + q;
-            const bool ok = (c < nchunks) && (p >= 0) && (p < m.na) &&
-                            (ARRAY_ENDS || cols[q] >= 0);
-            xv[u][q] = ok ? __ldg(x + cols[q]) : 0.0f;
+            if (ARRAY_ENDS) xv[u][q] = __ldg(x + cols[q]);
+            else xv[u][q] = cols[q] >= 0 ? __ldg(x + cols[q]) : 0.0f;
           }
         }
+      }
+      thread_search();
+      if (nchunks > 0) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int c = base + u * THREADS + t;
-          const int p0 = 4 * c - skew;
+          const int c = u * THREADS + t;
+          const int p0 = (c < nchunks ? 4 * c : -8) - skew;
           const float vals[4] = {cv[u].x, cv[u].y, cv[u].z, cv[u].w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int p = p0 + q;
-            if ((c < nchunks) && (p >= 0) && (p < m.na))
+            if (unsigned(p) < una)
               sm.prod[pad_index(p)] = __fmul_rn(vals[q], xv[u][q]);
+          }
+        }
+        // a non-zero skew spills at most one chunk past U*THREADS
+        if (t == 0 && nchunks > U * THREADS) {
+          const int c = U * THREADS;
+          const int4 i4 = sidx4[c];
+          const float4 v4 = sval4[c];
+          const int cols[4] = {i4.x, i4.y, i4.z, i4.w};
+          const float vals[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int p = 4 * c - skew + q;
+            if (unsigned(p) < una) {
+              const float xx = (ARRAY_ENDS || cols[q] >= 0) ? __ldg(x + cols[q]) : 0.0f;
+              sm.prod[pad_index(p)] = __fmul_rn(vals[q], xx);
+            }
           }
         }
       }
@@ -265,45 +314,51 @@ __global__ void __launch_bounds__(THREADS, 2)
         const float xx = (ARRAY_ENDS || col >= 0) ? __ldg(x + col) : 0.0f;
         sm.prod[pad_index(p)] = __fmul_rn(v, xx);
       }
+      thread_search();
     }
     __syncthreads();
+    lap(1);  // gather / multiply / search (incl. barrier)
 
     // ---------------- per-thread merge walk ----------------
-    const int items = m.nt + m.na;
-    int d = t * IPT;
-    if (d > items) d = items;
-    // Row end of tile-local row i, relative to the tile's first atom.
-    auto rel_end = [&](int i) -> int {
-      if (ARRAY_ENDS) return sre[m.skew_r + i] - m.sy;
-      return (m.sx + i + 1) * pitch - m.sy;
-    };
-    int lo = d - m.na; if (lo < 0) lo = 0;
-    int hi = d < m.nt ? d : m.nt;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (rel_end(mid) <= d - mid - 1) lo = mid + 1; else hi = mid;
-    }
-    int row = lo;
-    int atom = d - lo;
-    int rend = (row < m.nt) ? rel_end(row) : 0x7fffffff;
+    int budget = items - d;
+    if (budget > IPT) budget = IPT;
+    // All candidate products up front: IPT independent shared loads instead
+    // of a load->compare->load chain (reads past the thread's own atoms are
+    // harmless and unused).
+    float pr[IPT];
+#pragma unroll
+    for (int q = 0; q < IPT; ++q) pr[q] = sm.prod[pad_index(atom0 + q)];
+    // Two row ends are kept in registers: the one being watched and the one
+    // after it. Closing a row shifts them and re-loads the look-ahead with a
+    // shared load whose latency is not needed until the NEXT closing, so the
+    // common case (at most one row ends at a given atom) is straight-line,
+    // predicated code without a dependent load.
+    constexpr int kNever = 0x7fffffff;
+    int rend = (row < m.nt) ? rel_end(row) : kNever;
+    int rend1 = (row + 1 < m.nt) ? rel_end(row + 1) : kNever;
     float sum = 0.0f, head = 0.0f;
     int first_row = -1;
-    constexpr int kRowOutTop = shared_t::kProdWords - 1;
+    auto close_row = [&]() {
+      if (first_row < 0) { head = sum; first_row = row; }
+      else y[m.sx + row] = sum;        // row lies wholly inside this thread
+      sum = 0.0f;
+      ++row;
+      rend = rend1;
+      rend1 = (row + 1 < m.nt) ? rel_end(row + 1) : kNever;
+      --budget;
+    };
 #pragma unroll
     for (int q = 0; q < IPT; ++q) {
-      if (d + q < items) {
-        if (atom < rend) {
-          sum = __fadd_rn(sum, sm.prod[pad_index(atom)]);
-          ++atom;
-        } else {
-          if (first_row < 0) { head = sum; first_row = row; }
-          else sm.prod[kRowOutTop - row] = sum;
-          sum = 0.0f;
-          ++row;
-          rend = (row < m.nt) ? rel_end(row) : 0x7fffffff;
-        }
+      // rows that end at or before atom (atom0 + q) are closed first -- the
+      // same order the merge path visits them in
+      if (budget > 0 && rend <= atom0 + q) close_row();
+      while (budget > 0 && rend <= atom0 + q) close_row();   // empty rows
+      if (budget > 0) {
+        sum = __fadd_rn(sum, pr[q]);
+        --budget;
       }
     }
+    lap(2);  // walk
 
     // ---------------- segmented scan of (flag, value) over threads -------
     // combine(a, b) = (a.f | b.f, b.f ? b.v : a.v + b.v)
@@ -324,6 +379,17 @@ __global__ void __launch_bounds__(THREADS, 2)
     if (lane == 0) { ev = 0.0f; ef = 0; }
     if (lane == 31) { sm.warp_val[warp] = v; sm.warp_flag[warp] = f; }
     __syncthreads();
+    // Every thread is done with stage `st` (indices/values before the first
+    // barrier, row ends before this one): put the next tile in flight now.
+    if (t == 0 && issue_tile_id < num_cta_tiles) {
+      loops::tma::fence_proxy_async();
+      issue_tile<THREADS, TILE, STAGES, ARRAY_ENDS>(
+          sm, st, nxt_s, nxt_e, row_end, indices, values, T, A, policy);
+      issue_tile_id += stride;
+      if (issue_tile_id < num_cta_tiles)
+        load_coords(issue_tile_id);
+    }
+    lap(3);  // scan barrier + refill issue
     // what precedes this warp inside the CTA
     float wv = 0.0f; int wf = 0;
     for (int w = 0; w < warp; ++w) {
@@ -334,29 +400,21 @@ __global__ void __launch_bounds__(THREADS, 2)
     }
     const float carry_in = ef ? ev : __fadd_rn(wv, ev);
     if (first_row >= 0)
-      sm.prod[kRowOutTop - first_row] = __fadd_rn(carry_in, head);
+      y[m.sx + first_row] = __fadd_rn(carry_in, head);
     if (t == THREADS - 1) {
       // CTA-wide inclusive aggregate = the partial of the row the tile ends in.
       const float total = f ? v : __fadd_rn(wv, v);
       carry_row[j] = m.sx + m.nt;
       carry_val[j] = total;
     }
-    __syncthreads();
-
-    // ---------------- coalesced row stores ----------------
-    for (int i = t; i < m.nt; i += THREADS)
-      y[m.sx + i] = sm.prod[kRowOutTop - i];
-    __syncthreads();
-
-    // ---------------- refill the stage just drained ----------------
-    if (t == 0 && issue_tile_id < num_cta_tiles) {
-      loops::tma::fence_proxy_async();
-      issue_tile<THREADS, TILE, STAGES, ARRAY_ENDS>(
-          sm, st, nxt_s, nxt_e, row_end, indices, values, T, A, policy);
-      issue_tile_id += stride;
-      if (issue_tile_id < num_cta_tiles)
-        load_coords(issue_tile_id);
-    }
+    lap(4);  // cross-warp combine + row stores
+    // No barrier here: the next tile's first barrier orders the scratch reuse
+    // (warp_val/warp_flag are rewritten only after it, prod only before it by
+    // threads that have all passed the barrier above).
+  }
+  if (timing) {
+    for (int q = 0; q < 6; ++q) phase_cycles[blockIdx.x * 8 + q] = ph[q];
+    phase_cycles[blockIdx.x * 8 + 6] = k;
   }
 }
 
