@@ -1,25 +1,289 @@
-// loops_b200/csrc/bcsr_tc.cuh -- BCSR 4x4 bf16 SpMV on the tcgen05 tensor
-// cores (placeholder until the tensor-core kernel lands).
+// loops_b200/csrc/bcsr_tc.cuh -- BCSR 4x4, bf16 values and x, fp32 accumulate:
+// SpMV on the tcgen05 tensor cores (BASELINE.json config 4). Replaces, for this
+// dtype, reference algorithms/spmv/bcsr_thread_mapped.cuh:36-74 (one thread per
+// block-row doing 16 scalar FMAs per block).
+//
+// Mapping (a block really is a dense 4x4 contraction, a block-ROW is a
+// contraction over all of its blocks):
+//   * a GROUP is 32 block-rows; its 128 scalar rows are the M dimension of one
+//     UMMA tile: m = 4*b + i  (b = block-row slot 0..31, i = row inside block);
+//   * one K-step covers 4 consecutive blocks of every block-row of the group:
+//     k = 4*slot + j (slot 0..3, j = column inside block), K = 16 (bf16 UMMA K);
+//         A[m][k] = block(row_b, 4s + slot)[i][j]           (0 past the row end)
+//         B[n][k] = x[4*bcol(row_n, 4s + slot) + j]          (n = block-row slot)
+//     D[m][n] += sum_k A[m][k] B[n][k]; the wanted y values are the block
+//     diagonal n == m/4, everything else is discarded (N = 32 is the price of
+//     giving every block-row its own gathered x; tensor time stays far below
+//     HBM time: 16 cycles per 128 blocks);
+//   * the accumulator D (128 lanes x 32 columns fp32) lives in TMEM for the
+//     whole K loop of the group and is read once (tcgen05.ld) at the end;
+//   * block-rows are ordered by length (plan, data-independent of values) so
+//     the 32 rows of a group need nearly the same number of K-steps; groups are
+//     dealt longest-first to persistent CTAs.
+// A and B tiles are staged in shared memory in the canonical K-major
+// no-swizzle UMMA layout (8-row x 16-byte core matrices: LBO = 128 B between
+// the two K halves, SBO = 256 B between 8-row groups), double-buffered; reuse
+// is gated by tcgen05.commit -> mbarrier.
 #pragma once
+
 #include "common.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <loops/util/tma.hxx>
 
 namespace loopsb {
 namespace bcsr_tc {
 
+constexpr int kThreads = 128;       // 32 block-row slots x 4 block slots
+constexpr int kGroupRows = 32;
+constexpr int kTmemCols = 32;       // N = 32 fp32 accumulator columns
+constexpr int kATileBytes = 128 * 16 * 2;  // 4 KB
+constexpr int kBTileBytes = 32 * 16 * 2;   // 1 KB
+
 struct plan_data {
+  int num_block_rows = 0;
+  int num_groups = 0;
+  int* order = nullptr;       // block-row ids, longest first
+  int* lengths = nullptr;     // scratch (sorted lengths)
+  int sm_count = 0;
   long long bytes = 0;
 };
 
-inline int create(plan_data** out, const loopsb_layout_t*, int, cudaStream_t) {
-  *out = new plan_data();
+__global__ void row_lengths_kernel(const int* __restrict__ off, int n,
+                                   int* __restrict__ len, int* __restrict__ id) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) { len[r] = off[r + 1] - off[r]; id[r] = r; }
+}
+
+inline void destroy(plan_data* p) {
+  if (!p) return;
+  if (p->order) cudaFree(p->order);
+  if (p->lengths) cudaFree(p->lengths);
+  delete p;
+}
+
+inline long long workspace_bytes(const plan_data* p) { return p ? p->bytes : 0; }
+
+inline int create(plan_data** out, const loopsb_layout_t* lay, int sm_count,
+                  cudaStream_t stream) {
+  *out = nullptr;
+  plan_data* p = new plan_data();
+  p->num_block_rows = lay->num_tiles;
+  p->num_groups = (lay->num_tiles + kGroupRows - 1) / kGroupRows;
+  p->sm_count = sm_count;
+  const int n = lay->num_tiles;
+  if (n == 0) { *out = p; return LOOPSB_OK; }
+  int *len_in = nullptr, *id_in = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  auto fail = [&](const char* what) {
+    set_error("bcsr tensor-core plan: %s failed: %s", what, cudaGetErrorString(cudaGetLastError()));
+    cudaFree(len_in); cudaFree(id_in); cudaFree(tmp);
+    destroy(p);
+    return LOOPSB_ERR_CUDA;
+  };
+  if (cudaMalloc(&len_in, size_t(n) * 4) != cudaSuccess || cudaMalloc(&id_in, size_t(n) * 4) != cudaSuccess ||
+      cudaMalloc(&p->order, size_t(n) * 4) != cudaSuccess || cudaMalloc(&p->lengths, size_t(n) * 4) != cudaSuccess)
+    return fail("cudaMalloc");
+  row_lengths_kernel<<<(n + 255) / 256, 256, 0, stream>>>(lay->offsets, n, len_in, id_in);
+  if (cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, len_in, p->lengths, id_in, p->order, n,
+                                                0, 32, stream) != cudaSuccess)
+    return fail("cub sizing");
+  if (cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16) != cudaSuccess) return fail("cudaMalloc(tmp)");
+  if (cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, len_in, p->lengths, id_in, p->order, n, 0, 32,
+                                                stream) != cudaSuccess)
+    return fail("cub sort");
+  if (cudaStreamSynchronize(stream) != cudaSuccess) return fail("sync");
+  cudaFree(len_in); cudaFree(id_in); cudaFree(tmp);
+  p->bytes = (long long)n * 8;
+  *out = p;
   return LOOPSB_OK;
 }
-inline void destroy(plan_data* p) { delete p; }
-inline long long workspace_bytes(const plan_data* p) { return p ? p->bytes : 0; }
-inline int run(plan_data*, const loopsb_layout_t*, const uint16_t*, const int32_t*,
-               const uint16_t*, float*, int32_t, cudaStream_t) {
-  set_error("BCSR 4x4 bf16 tcgen05 kernel not built yet");
-  return LOOPSB_ERR_UNSUPPORTED;
+
+// ---- tcgen05 / TMEM wrappers (inline PTX) ---------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   loops::tma::smem_addr(smem_dst)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before_sync() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after_sync() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, one CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive when all previously issued MMAs of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   loops::tma::smem_addr(bar)) : "memory");
+}
+// 32 lanes x 8 consecutive 32-bit columns of this warp's TMEM quadrant.
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, no swizzle: 8x16B core matrices, LBO between K halves, SBO between
+// 8-row groups (cute::UMMA::SmemDescriptor, version 1).
+__device__ __forceinline__ uint64_t make_smem_desc(const void* tile, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const uint64_t addr = loops::tma::smem_addr(tile);
+  return ((addr >> 4) & 0x3FFFull) | (uint64_t((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         (uint64_t((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t tile_offset(int row, int slot) {
+  // byte offset of the 8-byte piece holding k = 4*slot .. 4*slot+3 of `row`
+  return uint32_t((row >> 3) * 256 + (row & 7) * 16 + (slot >> 1) * 128 + (slot & 1) * 8);
+}
+
+struct __align__(1024) tc_shared {
+  unsigned char a[2][kATileBytes];
+  unsigned char b[2][kBTileBytes];
+  unsigned long long mma_done[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads)
+    spmv_bcsr4x4_bf16_kernel(const int* __restrict__ block_offsets, const int* __restrict__ block_cols,
+                             const uint16_t* __restrict__ values, const uint16_t* __restrict__ x,
+                             float* __restrict__ y, const int* __restrict__ order, int num_block_rows,
+                             int num_groups, int num_rows) {
+  __shared__ tc_shared sm;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int b = tid >> 2;      // block-row slot inside the group
+  const int slot = tid & 3;    // block slot inside the K-step
+
+  if (warp == 0) tmem_alloc(&sm.tmem_base, kTmemCols);
+  if (tid == 0) {
+    loops::tma::barrier_init(reinterpret_cast<uint64_t*>(&sm.mma_done[0]), 1);
+    loops::tma::barrier_init(reinterpret_cast<uint64_t*>(&sm.mma_done[1]), 1);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+  constexpr uint32_t idesc = make_idesc(128, 32);
+
+  uint32_t uses[2] = {0u, 0u};  // completed-or-pending commits per buffer (same in every thread)
+
+  for (int g = blockIdx.x; g < num_groups; g += gridDim.x) {
+    const int slot_row = g * kGroupRows + b;
+    const int r = slot_row < num_block_rows ? __ldg(order + slot_row) : -1;
+    int start = 0, len = 0;
+    if (r >= 0) { start = __ldg(block_offsets + r); len = __ldg(block_offsets + r + 1) - start; }
+    // rows are sorted by length: slot 0 of the group is the longest
+    const int r0 = __ldg(order + g * kGroupRows);
+    const int len0 = __ldg(block_offsets + r0 + 1) - __ldg(block_offsets + r0);
+    const int steps = (len0 + 3) >> 2;
+
+    for (int s = 0; s < steps; ++s) {
+      const int buf = s & 1;
+      const int k = 4 * s + slot;
+      uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+      uint2 xs = make_uint2(0, 0);
+      if (k < len) {
+        const long long blk = (long long)start + k;
+        const int bc = __ldg(block_cols + blk);
+        const uint4* vp = reinterpret_cast<const uint4*>(values + blk * 16);
+        v0 = __ldg(vp);
+        v1 = __ldg(vp + 1);
+        xs = __ldg(reinterpret_cast<const uint2*>(x + (long long)bc * 4));
+      }
+      // the MMA that last read this buffer must have completed
+      if (uses[buf] > 0)
+        loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.mma_done[buf]), (uses[buf] - 1) & 1u);
+      unsigned char* A = sm.a[buf];
+      unsigned char* B = sm.b[buf];
+      *reinterpret_cast<uint2*>(A + tile_offset(4 * b + 0, slot)) = make_uint2(v0.x, v0.y);
+      *reinterpret_cast<uint2*>(A + tile_offset(4 * b + 1, slot)) = make_uint2(v0.z, v0.w);
+      *reinterpret_cast<uint2*>(A + tile_offset(4 * b + 2, slot)) = make_uint2(v1.x, v1.y);
+      *reinterpret_cast<uint2*>(A + tile_offset(4 * b + 3, slot)) = make_uint2(v1.z, v1.w);
+      *reinterpret_cast<uint2*>(B + tile_offset(b, slot)) = xs;
+      loops::tma::fence_proxy_async();   // generic-proxy smem writes -> tensor-core (async) proxy
+      tc_fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after_sync();
+        umma_bf16(tmem, make_smem_desc(A, 128, 256), make_smem_desc(B, 128, 256), idesc, s > 0 ? 1u : 0u);
+        umma_commit(reinterpret_cast<uint64_t*>(&sm.mma_done[buf]));
+      }
+      uses[buf] += 1;
+    }
+
+    if (steps > 0) {
+      // accumulator complete when the last commit lands
+      const int last = (steps - 1) & 1;
+      loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.mma_done[last]), (uses[last] - 1) & 1u);
+      // the other buffer's commit (if any) was issued earlier, so it has landed too
+      tc_fence_after_sync();
+      // lane l of warp w holds scalar row m = 32w + l; its block-row slot is
+      // m/4 = 8w + l/4, i.e. column (l/4) of the 8-column window at 8w.
+      uint32_t acc[8];
+      tmem_ld_32x32b_x8(tmem + (uint32_t(32 * warp) << 16) + uint32_t(8 * warp), acc);
+      const int m = 32 * warp + lane;
+      float out = 0.0f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if ((lane >> 2) == q) out = __uint_as_float(acc[q]);
+      const int rr_slot = g * kGroupRows + (m >> 2);
+      if (rr_slot < num_block_rows) {
+        const long long row = (long long)__ldg(order + rr_slot) * 4 + (m & 3);
+        if (row < num_rows) y[row] = out;
+      }
+      tc_fence_before_sync();
+    } else {
+      // every block-row of the group is empty
+      const int m = 32 * warp + lane;
+      const int rr_slot = g * kGroupRows + (m >> 2);
+      if (rr_slot < num_block_rows) {
+        const long long row = (long long)__ldg(order + rr_slot) * 4 + (m & 3);
+        if (row < num_rows) y[row] = 0.0f;
+      }
+    }
+    __syncthreads();   // TMEM and both buffers are free for the next group
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+inline int run(plan_data* p, const loopsb_layout_t* lay, const uint16_t* values, const int32_t* block_cols,
+               const uint16_t* x, float* y, int32_t num_rows, cudaStream_t stream) {
+  LOOPSB_REQUIRE(p != nullptr && lay != nullptr, "null plan");
+  LOOPSB_REQUIRE(num_rows >= 0, "negative rows");
+  if (num_rows == 0 || p->num_block_rows == 0) return LOOPSB_OK;
+  LOOPSB_REQUIRE(y != nullptr, "y is null");
+  LOOPSB_REQUIRE(lay->num_atoms == 0 || (values && block_cols && x), "null matrix / x pointer");
+  LOOPSB_REQUIRE((reinterpret_cast<uintptr_t>(values) & 15u) == 0 && (reinterpret_cast<uintptr_t>(x) & 7u) == 0,
+                 "values must be 16-byte and x 8-byte aligned");
+  int grid = p->sm_count * 8;
+  if (grid > p->num_groups) grid = p->num_groups;
+  spmv_bcsr4x4_bf16_kernel<<<grid, kThreads, 0, stream>>>(lay->offsets, block_cols, values, x, y, p->order,
+                                                        p->num_block_rows, p->num_groups, num_rows);
+  LOOPSB_CUDA_TRY(cudaGetLastError());
+  return LOOPSB_OK;
 }
 
 }  // namespace bcsr_tc

@@ -1,0 +1,98 @@
+"""GPU parity of the BCSR 4x4 bf16 tcgen05 path (BASELINE config 4) against the
+oracle's fp32-accumulating restatement of the reference kernel's loop
+(algorithms/spmv/bcsr_thread_mapped.cuh:48-62) on bf16-rounded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import random_csr
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(oracle, rows, cols, off, idx, val, x, exact):
+    from loops_b200 import csr_t, bcsr_t
+    from loops_b200.algorithms import spmv
+    A = csr_t(rows, cols, off, idx, val)
+    B = bcsr_t.from_csr(A, 4, 4, value_dtype=torch.bfloat16)
+    xb = B.padded_x(torch.as_tensor(x).cuda().to(torch.bfloat16))
+    y = torch.full((rows,), float("nan"), device="cuda")
+    spmv.bcsr_thread_mapped(B, xb, y)
+    y = y.cpu().numpy()
+    # oracle on the SAME bf16-rounded numbers, fp32 accumulate
+    b_off = B.block_offsets.cpu().numpy()
+    b_col = B.block_col_indices.cpu().numpy()
+    b_val = B.values.float().cpu().numpy()
+    xr = xb.float().cpu().numpy()
+    ref = oracle.spmv_bcsr(4, 4, rows, b_off, b_col, b_val, xr)
+    assert np.all(np.isfinite(y))
+    if exact:
+        np.testing.assert_array_equal(y, ref)
+    else:
+        # products of two bf16 are exact in fp32; only the order of the fp32
+        # adds differs -> 1e-6 relative to the row's L1 mass
+        l1 = np.zeros(rows, np.float64)
+        nbr = len(b_off) - 1
+        for br in range(nbr):
+            for b in range(b_off[br], b_off[br + 1]):
+                blk = np.abs(b_val[b * 16:(b + 1) * 16].reshape(4, 4).astype(np.float64))
+                xs = np.abs(xr[b_col[b] * 4: b_col[b] * 4 + 4].astype(np.float64))
+                for i in range(4):
+                    if br * 4 + i < rows:
+                        l1[br * 4 + i] += float(blk[i] @ xs)
+        err = np.abs(y.astype(np.float64) - ref.astype(np.float64)) / np.maximum(l1, 1e-30)
+        assert err.max() <= 1e-6, float(err.max())
+
+
+def test_battery_bf16(oracle, battery):
+    for b in battery:
+        _run(oracle, b["rows"], b["cols"], b["off"], b["idx"], b["val"], b["x"], exact=False)
+
+
+@pytest.mark.parametrize("rows,cols,dens,seed,empty,heavy", [
+    (1, 7, 0.9, 1, 0, None), (130, 130, 0.05, 2, 0, None), (257, 1000, 0.01, 3, 3, (100, 1000)),
+    (4096, 4096, 0.004, 4, 0, (7, 4096)), (1000, 64, 0.0, 5, 0, (500, 64)), (333, 4001, 0.02, 6, 2, None)])
+def test_shapes_exact(oracle, rows, cols, dens, seed, empty, heavy):
+    off, idx, val = random_csr(rows, cols, dens, seed, empty, heavy, exact=True)
+    x = np.random.default_rng(seed).integers(1, 11, cols).astype(np.float32)
+    _run(oracle, rows, cols, off, idx, val, x, exact=True)
+
+
+def test_powerlaw_blocks_exact(oracle):
+    """Config-4-shaped input at 1/64 scale: power-law block-row lengths."""
+    from loops_b200 import generate as g
+    nbr = 4096
+    off, bcol, _ = g.synth_csr(nbr, nbr, nbr * 32)         # block structure
+    off, bcol = off.numpy(), bcol.numpy()
+    rows = cols = nbr * 4
+    # expand every block to a dense 4x4 of k/8 values -> CSR
+    nb = len(bcol)
+    rng = np.random.default_rng(9)
+    vals = (rng.integers(1, 17, size=(nb, 4, 4)) / 8.0).astype(np.float32)
+    deg = np.diff(off)
+    csr_off = np.zeros(rows + 1, np.int64)
+    csr_off[1:] = np.cumsum(np.repeat(deg * 4, 4))
+    idx = np.empty(nb * 16, np.int32); val = np.empty(nb * 16, np.float32)
+    p = 0
+    for br in range(nbr):
+        blks = np.arange(off[br], off[br + 1])
+        for i in range(4):
+            n = len(blks) * 4
+            idx[p:p + n] = (bcol[blks][:, None] * 4 + np.arange(4)[None, :]).reshape(-1)
+            val[p:p + n] = vals[blks, i, :].reshape(-1)
+            p += n
+    x = g.x_recipe(cols).numpy()
+    _run(oracle, rows, cols, csr_off.astype(np.int32), idx, val, x, exact=True)
+
+
+def test_fp32_blocks_still_use_thread_mapped(oracle, battery):
+    from loops_b200 import csr_t, bcsr_t
+    from loops_b200.algorithms import spmv
+    b = battery[3]
+    A = csr_t(b["rows"], b["cols"], b["off"], b["idx"], b["val"])
+    B = bcsr_t.from_csr(A, 4, 4)
+    y = torch.empty(b["rows"], device="cuda")
+    spmv.bcsr_thread_mapped(B, B.padded_x(torch.as_tensor(b["x"]).cuda()), y)
+    g_off, g_col, g_val = b["bcsr4"]
+    xp = np.zeros(((b["cols"] + 3) // 4) * 4, np.float32); xp[: b["cols"]] = b["x"]
+    np.testing.assert_array_equal(y.cpu().numpy(), oracle.spmv_bcsr(4, 4, b["rows"], g_off, g_col, g_val, xp))
