@@ -168,3 +168,66 @@ class bcsr_t(_planned):
         out = torch.zeros(n, dtype=x.dtype, device=x.device)
         out[: x.numel()] = x
         return out
+
+
+def _attach_from_tensors():
+    """Zero-copy constructors for data that already lives on the device."""
+
+    def coo_from_tensors(cls, rows, cols, row_indices, col_indices, values):
+        self = cls.__new__(cls)
+        _planned.__init__(self)
+        self.rows, self.cols = int(rows), int(cols)
+        self.row_indices, self.col_indices, self.values = row_indices, col_indices, values
+        self.nnzs = int(values.numel())
+        return self
+
+    def ell_from_tensors(cls, rows, cols, nnzs, pitch, indices, values):
+        self = cls.__new__(cls)
+        _planned.__init__(self)
+        self.rows, self.cols, self.nnzs, self.pitch = int(rows), int(cols), int(nnzs), int(pitch)
+        self.indices, self.values = indices, values
+        return self
+
+    def bcsr_from_tensors(cls, R, C, rows, cols, nnzs, block_offsets, block_col_indices, values):
+        self = cls.__new__(cls)
+        _planned.__init__(self)
+        self.R, self.C = int(R), int(C)
+        self.rows, self.cols, self.nnzs = int(rows), int(cols), int(nnzs)
+        self.num_block_rows = (self.rows + self.R - 1) // self.R
+        self.num_block_cols = (self.cols + self.C - 1) // self.C
+        self.block_offsets, self.block_col_indices, self.values = block_offsets, block_col_indices, values
+        self.num_blocks = int(block_col_indices.numel())
+        return self
+
+    coo_t.from_tensors = classmethod(coo_from_tensors)
+    ell_t.from_tensors = classmethod(ell_from_tensors)
+    bcsr_t.from_tensors = classmethod(bcsr_from_tensors)
+
+
+_attach_from_tensors()
+
+
+def csr_to_coo_device(csr: "csr_t") -> "coo_t":
+    """CSR -> COO on the device (row ids by expanding the offsets)."""
+    deg = (csr.offsets[1:] - csr.offsets[:-1]).long()
+    rows_of = torch.repeat_interleave(torch.arange(csr.rows, device=csr.values.device, dtype=torch.int32), deg,
+                                      output_size=csr.nnzs)
+    return coo_t.from_tensors(csr.rows, csr.cols, rows_of, csr.indices, csr.values)
+
+
+def csr_to_ell_device(csr: "csr_t") -> "ell_t":
+    """CSR -> ELL on the device: pitch = widest row, padding column -1 / value 0
+    (same rules as the reference's host converter, ell.hxx:113-145)."""
+    dev = csr.values.device
+    off = csr.offsets.long()
+    deg = off[1:] - off[:-1]
+    pitch = int(deg.max().item()) if csr.rows else 0
+    e_idx = torch.full((csr.rows * pitch,), -1, dtype=torch.int32, device=dev)
+    e_val = torch.zeros(csr.rows * pitch, dtype=torch.float32, device=dev)
+    if csr.nnzs:
+        row_of = torch.repeat_interleave(torch.arange(csr.rows, device=dev), deg, output_size=csr.nnzs)
+        slot = torch.arange(csr.nnzs, device=dev) - off[row_of]
+        dst = row_of * pitch + slot
+        e_idx[dst] = csr.indices
+        e_val[dst] = csr.values
+    return ell_t.from_tensors(csr.rows, csr.cols, csr.nnzs, pitch, e_idx, e_val)

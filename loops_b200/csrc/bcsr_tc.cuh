@@ -28,6 +28,8 @@
 
 #include "common.cuh"
 
+#include <vector>
+
 #include <cub/device/device_radix_sort.cuh>
 #include <loops/util/tma.hxx>
 
@@ -40,11 +42,20 @@ constexpr int kTmemCols = 32;       // N = 32 fp32 accumulator columns
 constexpr int kATileBytes = 128 * 16 * 2;  // 4 KB
 constexpr int kBTileBytes = 32 * 16 * 2;   // 1 KB
 
+constexpr int kChunkSteps = 16;     // K-steps (of 4 blocks per row) per work item
+
 struct plan_data {
   int num_block_rows = 0;
   int num_groups = 0;
   int* order = nullptr;       // block-row ids, longest first
-  int* lengths = nullptr;     // scratch (sorted lengths)
+  int* lengths = nullptr;     // sorted lengths (device)
+  // Work items: a group's K loop cut into chunks of <= kChunkSteps steps so
+  // that a 1024-block row does not serialise inside one CTA.
+  int num_items = 0;
+  int4* items = nullptr;      // {group, first step, past-last step, partial slot or -1}
+  int num_split = 0;
+  int4* split = nullptr;      // {group, first partial slot, number of chunks, 0}
+  float* partial = nullptr;   // [slots][128] fp32
   int sm_count = 0;
   long long bytes = 0;
 };
@@ -59,6 +70,9 @@ inline void destroy(plan_data* p) {
   if (!p) return;
   if (p->order) cudaFree(p->order);
   if (p->lengths) cudaFree(p->lengths);
+  if (p->items) cudaFree(p->items);
+  if (p->split) cudaFree(p->split);
+  if (p->partial) cudaFree(p->partial);
   delete p;
 }
 
@@ -95,7 +109,40 @@ inline int create(plan_data** out, const loopsb_layout_t* lay, int sm_count,
     return fail("cub sort");
   if (cudaStreamSynchronize(stream) != cudaSuccess) return fail("sync");
   cudaFree(len_in); cudaFree(id_in); cudaFree(tmp);
-  p->bytes = (long long)n * 8;
+  len_in = id_in = nullptr; tmp = nullptr;
+  // Work-item tables (host): only the longest row of every group matters.
+  std::vector<int> lens(static_cast<size_t>(n), 0);
+  if (cudaMemcpy(lens.data(), p->lengths, size_t(n) * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return fail("cudaMemcpy(lengths)");
+  std::vector<int4> items, split;
+  int slots = 0;
+  for (int g = 0; g < p->num_groups; ++g) {
+    const int steps = (lens[size_t(g) * kGroupRows] + 3) >> 2;
+    const int nch = steps > kChunkSteps ? (steps + kChunkSteps - 1) / kChunkSteps : 1;
+    if (nch == 1) {
+      items.push_back(make_int4(g, 0, steps, -1));
+    } else {
+      split.push_back(make_int4(g, slots, nch, 0));
+      for (int c = 0; c < nch; ++c) {
+        const int s0 = c * kChunkSteps;
+        const int s1 = s0 + kChunkSteps < steps ? s0 + kChunkSteps : steps;
+        items.push_back(make_int4(g, s0, s1, slots++));
+      }
+    }
+  }
+  p->num_items = int(items.size());
+  p->num_split = int(split.size());
+  if (cudaMalloc(&p->items, items.size() * sizeof(int4)) != cudaSuccess) return fail("cudaMalloc(items)");
+  if (cudaMemcpy(p->items, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess)
+    return fail("cudaMemcpy(items)");
+  if (!split.empty()) {
+    if (cudaMalloc(&p->split, split.size() * sizeof(int4)) != cudaSuccess ||
+        cudaMalloc(&p->partial, size_t(slots) * 128 * sizeof(float)) != cudaSuccess)
+      return fail("cudaMalloc(split)");
+    if (cudaMemcpy(p->split, split.data(), split.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess)
+      return fail("cudaMemcpy(split)");
+  }
+  p->bytes = (long long)n * 8 + (long long)items.size() * 16 + (long long)split.size() * 16 + (long long)slots * 512;
   *out = p;
   return LOOPSB_OK;
 }
@@ -167,7 +214,8 @@ __global__ void __launch_bounds__(kThreads)
     spmv_bcsr4x4_bf16_kernel(const int* __restrict__ block_offsets, const int* __restrict__ block_cols,
                              const uint16_t* __restrict__ values, const uint16_t* __restrict__ x,
                              float* __restrict__ y, const int* __restrict__ order, int num_block_rows,
-                             int num_groups, int num_rows) {
+                             const int4* __restrict__ items, int num_items, float* __restrict__ partial,
+                             int num_rows) {
   __shared__ tc_shared sm;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -187,17 +235,18 @@ __global__ void __launch_bounds__(kThreads)
 
   uint32_t uses[2] = {0u, 0u};  // completed-or-pending commits per buffer (same in every thread)
 
-  for (int g = blockIdx.x; g < num_groups; g += gridDim.x) {
+  for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+    const int4 item = __ldg(items + it);
+    const int g = item.x;
     const int slot_row = g * kGroupRows + b;
     const int r = slot_row < num_block_rows ? __ldg(order + slot_row) : -1;
     int start = 0, len = 0;
     if (r >= 0) { start = __ldg(block_offsets + r); len = __ldg(block_offsets + r + 1) - start; }
-    // rows are sorted by length: slot 0 of the group is the longest
-    const int r0 = __ldg(order + g * kGroupRows);
-    const int len0 = __ldg(block_offsets + r0 + 1) - __ldg(block_offsets + r0);
-    const int steps = (len0 + 3) >> 2;
+    // rows are sorted by length; the plan cut the longest row's K loop into
+    // [item.y, item.z)
+    const int steps = item.z - item.y;
 
-    for (int s = 0; s < steps; ++s) {
+    for (int s = item.y; s < item.z; ++s) {
       const int buf = s & 1;
       const int k = 4 * s + slot;
       uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
@@ -225,7 +274,7 @@ __global__ void __launch_bounds__(kThreads)
       __syncthreads();
       if (tid == 0) {
         tc_fence_after_sync();
-        umma_bf16(tmem, make_smem_desc(A, 128, 256), make_smem_desc(B, 128, 256), idesc, s > 0 ? 1u : 0u);
+        umma_bf16(tmem, make_smem_desc(A, 128, 256), make_smem_desc(B, 128, 256), idesc, s > item.y ? 1u : 0u);
         umma_commit(reinterpret_cast<uint64_t*>(&sm.mma_done[buf]));
       }
       uses[buf] += 1;
@@ -233,7 +282,7 @@ __global__ void __launch_bounds__(kThreads)
 
     if (steps > 0) {
       // accumulator complete when the last commit lands
-      const int last = (steps - 1) & 1;
+      const int last = (item.z - 1) & 1;
       loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.mma_done[last]), (uses[last] - 1) & 1u);
       // the other buffer's commit (if any) was issued earlier, so it has landed too
       tc_fence_after_sync();
@@ -246,10 +295,14 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         if ((lane >> 2) == q) out = __uint_as_float(acc[q]);
-      const int rr_slot = g * kGroupRows + (m >> 2);
-      if (rr_slot < num_block_rows) {
-        const long long row = (long long)__ldg(order + rr_slot) * 4 + (m & 3);
-        if (row < num_rows) y[row] = out;
+      if (item.w >= 0) {
+        partial[(long long)item.w * 128 + m] = out;   // this chunk's share, reduced in order later
+      } else {
+        const int rr_slot = g * kGroupRows + (m >> 2);
+        if (rr_slot < num_block_rows) {
+          const long long row = (long long)__ldg(order + rr_slot) * 4 + (m & 3);
+          if (row < num_rows) y[row] = out;
+        }
       }
       tc_fence_before_sync();
     } else {
@@ -269,6 +322,22 @@ __global__ void __launch_bounds__(kThreads)
   if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
 
+// y[row] = sum over the chunks of a split group, in chunk order.
+__global__ void __launch_bounds__(128)
+    bcsr_split_reduce_kernel(const int4* __restrict__ split, const float* __restrict__ partial,
+                             const int* __restrict__ order, int num_block_rows, int num_rows,
+                             float* __restrict__ y) {
+  const int4 s = __ldg(split + blockIdx.x);
+  const int m = threadIdx.x;
+  float acc = 0.0f;
+  for (int c = 0; c < s.z; ++c) acc = __fadd_rn(acc, partial[(long long)(s.y + c) * 128 + m]);
+  const int rr_slot = s.x * kGroupRows + (m >> 2);
+  if (rr_slot < num_block_rows) {
+    const long long row = (long long)__ldg(order + rr_slot) * 4 + (m & 3);
+    if (row < num_rows) y[row] = acc;
+  }
+}
+
 inline int run(plan_data* p, const loopsb_layout_t* lay, const uint16_t* values, const int32_t* block_cols,
                const uint16_t* x, float* y, int32_t num_rows, cudaStream_t stream) {
   LOOPSB_REQUIRE(p != nullptr && lay != nullptr, "null plan");
@@ -279,10 +348,16 @@ inline int run(plan_data* p, const loopsb_layout_t* lay, const uint16_t* values,
   LOOPSB_REQUIRE((reinterpret_cast<uintptr_t>(values) & 15u) == 0 && (reinterpret_cast<uintptr_t>(x) & 7u) == 0,
                  "values must be 16-byte and x 8-byte aligned");
   int grid = p->sm_count * 8;
-  if (grid > p->num_groups) grid = p->num_groups;
+  if (grid > p->num_items) grid = p->num_items;
   spmv_bcsr4x4_bf16_kernel<<<grid, kThreads, 0, stream>>>(lay->offsets, block_cols, values, x, y, p->order,
-                                                        p->num_block_rows, p->num_groups, num_rows);
+                                                        p->num_block_rows, p->items, p->num_items, p->partial,
+                                                        num_rows);
   LOOPSB_CUDA_TRY(cudaGetLastError());
+  if (p->num_split > 0) {
+    bcsr_split_reduce_kernel<<<p->num_split, 128, 0, stream>>>(p->split, p->partial, p->order, p->num_block_rows,
+                                                             num_rows, y);
+    LOOPSB_CUDA_TRY(cudaGetLastError());
+  }
   return LOOPSB_OK;
 }
 

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kGroupThreads)
 
 // ----------------------------------------------------------- work oriented --
 constexpr int kWorkThreads = 128;
-constexpr int kWorkWindow = 6144;  // staged row ends per block (24 KB)
+constexpr int kWorkWindow = 1016;  // staged row ends per block (4 KB: keeps 16 blocks/SM inside the 100 KB carve-out)
 
 __device__ __forceinline__ void work_search(long long d, const int* ends,
                                             long long ends_first, long long lo_x,
@@ -229,7 +229,17 @@ __global__ void __launch_bounds__(kWorkThreads)
   long long cur = sy;
   for (long long row = sx; row < ex; ++row) {
     const long long stop = ends[row - ends_first];
-    for (long long nz = cur; nz < stop; ++nz)
+    long long nz = cur;
+    for (; nz + 4 <= stop; nz += 4) {   // four independent index->x chains
+      const int c0 = __ldg(indices + nz), c1 = __ldg(indices + nz + 1);
+      const int c2 = __ldg(indices + nz + 2), c3 = __ldg(indices + nz + 3);
+      const float x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+      sum += __ldg(values + nz) * x0;
+      sum += __ldg(values + nz + 1) * x1;
+      sum += __ldg(values + nz + 2) * x2;
+      sum += __ldg(values + nz + 3) * x3;
+    }
+    for (; nz < stop; ++nz)
       sum += __ldg(values + nz) * __ldg(x + __ldg(indices + nz));
     cur = stop;
     if (first_tile) {
