@@ -193,7 +193,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n):
@@ -206,6 +206,17 @@ def workload_config(n):
                         "one NCCL all-gather of x per step (BASELINE configs[4])",
             "rows": CFG5["rows"], "nnz": CFG5["nnz"], "schedule": "merge_path_flat", "layout": "csr",
             "l2": "inputs_exceed_l2", "partition": f"row{n}", "collective": "nccl all_gather(x)"}
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+# Libraries (NCCL's version banner, torchrun notices) must not pollute stdout:
+# keep a private handle on it and point fd 1 at stderr for everything else.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -367,7 +378,7 @@ def main():
                      "smem_bytes": info.smem_bytes, "merge_tiles": int(info.num_merge_tiles)},
             "y_checksum": chk,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if N > 1:
         dist.destroy_process_group()
 
