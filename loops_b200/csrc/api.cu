@@ -9,6 +9,7 @@
 
 #include <cstdarg>
 #include <cstdlib>
+#include <vector>
 #include <mutex>
 #include <new>
 
@@ -144,6 +145,7 @@ struct loopsb_plan {
   long long M = 0;
   int num_cta_tiles = 0;
   int variant = 0;
+  int wo_grid = 0;   // work_oriented: reference-style grid (blocks of 128 threads)
   long long* phases = nullptr;  // LOOPSB_DEBUG_PHASES=1: per-CTA phase cycle counters
   int* carry_row = nullptr;
   float* carry_val = nullptr;
@@ -350,12 +352,63 @@ int loopsb_plan_create(loopsb_plan_t** out, const loopsb_layout_t* lay,
       set_error("work_oriented SpMV exists for CSR (reference has no other)");
       return fail(LOOPSB_ERR_UNSUPPORTED);
     }
+    // Schedule geometry as the reference: N = occupancy grid x 128 threads,
+    // every thread owns w = ceil(W / N) consecutive merge items, so block B
+    // owns items [128 w B, 128 w (B+1)). The SpMV runs each block's range
+    // through the cooperative merge-tile kernel in pieces of <= 1024 items:
+    // same partition at block granularity, deterministic, y overwritten.
     int g = 0;
     int rc = loopsb_work_oriented_grid(&g);
     if (rc != LOOPSB_OK) return fail(rc);
-    p->cta_threads = sk::kWorkThreads;
-    p->grid = g;
-    p->launches = 2;  // memset + kernel
+    p->wo_grid = g;
+    const long long W = (long long)T + A;
+    const long long N = (long long)g * sk::kWorkThreads;
+    const long long w = (W + N - 1) / N;
+    const long long per_block = w * sk::kWorkThreads;
+    std::vector<long long> diags;
+    if (W > 0) {
+      for (long long d0 = 0; d0 < W; d0 += per_block) {
+        const long long d1 = d0 + per_block < W ? d0 + per_block : W;
+        for (long long d = d0; d < d1; d += mp::kRefItemsPerMergeTile) diags.push_back(d);
+      }
+      diags.push_back(W);
+    }
+    p->variant = merge_variant_from_env();
+    const merge_variant& mv = kMergeVariants[p->variant];
+    if (mv.g != 1) { p->variant = 9; }
+    const merge_variant& mv1 = kMergeVariants[p->variant];
+    p->M = diags.empty() ? 0 : (long long)diags.size() - 1;
+    p->num_cta_tiles = int(p->M);
+    p->cta_threads = mv1.threads;
+    p->smem_bytes = mv1.smem;
+    p->launches = 2;
+    int grid = mv1.ctas_per_sm * dp->sm_count;
+    if (grid > p->num_cta_tiles) grid = p->num_cta_tiles;
+    p->grid = grid;
+    if (p->M > 0) {
+      long long* d_diags = nullptr;
+      const size_t nct = size_t(p->num_cta_tiles);
+      if (cudaMalloc(&d_diags, diags.size() * sizeof(long long)) != cudaSuccess ||
+          cudaMalloc(&p->coords, size_t(p->M + 1) * sizeof(int2)) != cudaSuccess ||
+          cudaMalloc(&p->carry_row, nct * sizeof(int)) != cudaSuccess ||
+          cudaMalloc(&p->carry_val, nct * sizeof(float)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        cudaFree(d_diags);
+        set_error("device allocation of the work_oriented workspace failed");
+        return fail(LOOPSB_ERR_ALLOC);
+      }
+      cudaMemcpyAsync(d_diags, diags.data(), diags.size() * sizeof(long long), cudaMemcpyHostToDevice, s);
+      const int threads = 128;
+      mp::merge_coords_kernel<true><<<int((p->M + 1 + threads - 1) / threads), threads, 0, s>>>(
+          lay->offsets + 1, 0, T, A, 0, int(p->M), p->coords, d_diags);
+      cudaError_t e = cudaStreamSynchronize(s);   // diags (host vector) and d_diags die here
+      cudaFree(d_diags);
+      if (e != cudaSuccess || mv1.prepare(p->smem_bytes) != cudaSuccess) {
+        set_error("work_oriented plan set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(LOOPSB_ERR_CUDA);
+      }
+      p->workspace_bytes = (long long)(size_t(p->M + 1) * sizeof(int2) + nct * 8);
+    }
   }
   *out = p;
   return LOOPSB_OK;
@@ -496,11 +549,14 @@ int loopsb_spmv_f32(loopsb_plan_t* plan, const float* values,
     }
     case LOOPSB_SCHED_WORK_ORIENTED: {
       LOOPSB_REQUIRE(T == num_rows, "layout tiles must equal num_rows");
-      LOOPSB_CUDA_TRY(cudaMemsetAsync(y, 0, size_t(num_rows) * sizeof(float), s));
+      const int nct = plan->num_cta_tiles;
+      const merge_variant& mv = kMergeVariants[plan->variant];
       probe_scope probe(plan, s);
-      sk::spmv_work_oriented_csr<<<plan->grid, sk::kWorkThreads, 0, s>>>(
-          lay.offsets, col_indices, values, x, y, num_rows, A);
+      mv.launch(true, plan->grid, plan->smem_bytes, s, lay.offsets + 1, 0, col_indices, values, x, y,
+                plan->coords, int(plan->M), T, A, nct, plan->carry_row, plan->carry_val, nullptr);
       probe.close();
+      LOOPSB_CUDA_TRY(cudaGetLastError());
+      mp::spmv_merge_fixup_kernel<<<(nct + 255) / 256, 256, 0, s>>>(plan->carry_row, plan->carry_val, nct, T, y);
       LOOPSB_CUDA_TRY(cudaGetLastError());
       return LOOPSB_OK;
     }

@@ -435,13 +435,17 @@ __global__ void spmv_merge_fixup_kernel(const int* __restrict__ carry_row,
 }
 
 // coords[b] = S(b * items_per_merge_tile), b = 0..M, for array / pitch ends.
+// With `diagonals` (M+1 ascending values) the cut points are arbitrary -- used
+// by work_oriented, whose block boundaries are multiples of its per-thread
+// share rather than of the merge-tile size.
 template <bool ARRAY_ENDS>
 __global__ void merge_coords_kernel(const int* __restrict__ row_end, int pitch,
                                     int T, int A, long long items, int M,
-                                    int2* __restrict__ coords) {
+                                    int2* __restrict__ coords,
+                                    const long long* __restrict__ diagonals = nullptr) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b > M) return;
-  const long long d = (long long)b * items;
+  const long long d = diagonals ? diagonals[b] : (long long)b * items;
   long long lo = d - A; if (lo < 0) lo = 0;
   long long hi = d < T ? d : (long long)T;
   const long long x_min = lo;
