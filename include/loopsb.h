@@ -170,6 +170,60 @@ int loopsb_spmv_bcsr4x4_bf16(loopsb_plan_t* plan, const uint16_t* values_bf16,
                              const uint16_t* x_bf16_padded, float* y,
                              int32_t num_rows, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Band-tiled plan (optional accelerator for merge_path_flat / CSR).
+ * Still the reference's merge_path::preprocess_t idea -- per-matrix set-up that
+ * the timed SpMV re-uses (schedule/merge_path_flat.hxx:92-172; the reference's
+ * timer excludes it, algorithms/spmv/merge_path_flat.cuh:111,121-122) -- taken
+ * one step further: the plan keeps a re-ordered COPY of the matrix cut into
+ * (row block x column band) tiles (8 bytes per nonzero, as CSR) so that the
+ * SpMV kernel can hold its y rows and the current x band in shared memory
+ * (loops_b200/csrc/spmv_tiled.cuh). The call signature of the SpMV does not
+ * change: loopsb_spmv_f32 on this plan takes the tiled kernel whenever it is
+ * handed the SAME col_indices / values pointers the copy was made from (and a
+ * 16-byte aligned x); any other pointers run the plain CSR kernel. If the
+ * caller changes values in place it must call loopsb_plan_tile_csr again.
+ *
+ * flags bit 0 (LOOPSB_TILE_FORCE): build even when the cost model says the
+ * plain kernel is the better choice (x too large for the band walk to pay).
+ * Returns LOOPSB_ERR_UNSUPPORTED (plan unchanged, still usable) when the
+ * matrix does not fit the format or is not worth tiling. Synchronises.
+ * ------------------------------------------------------------------------- */
+#define LOOPSB_TILE_FORCE 1
+
+typedef struct loopsb_tiled_info {
+  int32_t nb, q, warps, cb, xb, es;   /* row blocks, column parts, consumer warps,
+                                         band width, x-ring depth, stream-ring depth */
+  int32_t rb, rw, cq, nband;          /* rows/block, rows/warp, columns/part, bands/part */
+  int32_t grid_blocks, cta_threads, smem_bytes, reserved;
+  int64_t total_steps;                /* 1 KB steps (128 entries) in the copy   */
+  int64_t real_entries, pad_entries;  /* nnz and padding entries                */
+  int64_t flagged_entries, flagged_steps; /* same-row lane collisions (slow path) */
+  int64_t bytes;                      /* device memory held by the copy         */
+} loopsb_tiled_info_t;
+
+int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices,
+                         const float* values, int32_t num_cols, int32_t flags,
+                         void* stream);
+int loopsb_plan_untile(loopsb_plan_t* plan);
+/* LOOPSB_ERR_UNSUPPORTED when the plan holds no tiled copy. */
+int loopsb_plan_tiled_info(const loopsb_plan_t* plan, loopsb_tiled_info_t* info);
+
+/* The same builder on HOST arrays, no device involved: returns the image the
+ * plan would upload, for format tests. geometry = {nb,q,warps,cb,xb,es}. */
+typedef struct loopsb_tiled_image loopsb_tiled_image_t;
+int loopsb_tiled_image_build_host(int32_t num_rows, int32_t num_cols,
+                                  const int32_t* host_offsets,
+                                  const int32_t* host_indices,
+                                  const float* host_values,
+                                  const int32_t geometry[6],
+                                  loopsb_tiled_image_t** out);
+int loopsb_tiled_image_info(const loopsb_tiled_image_t* img, loopsb_tiled_info_t* info);
+int loopsb_tiled_image_arrays(const loopsb_tiled_image_t* img, const uint32_t** steps,
+                              const int32_t** stream_base, const uint16_t** first_step,
+                              const uint16_t** last_step_end);
+int loopsb_tiled_image_free(loopsb_tiled_image_t* img);
+
 /* Host-buffer convenience with the flow of the reference's example mains
  * (examples/spmv/merge_path.cu:17-50): upload CSR + x, run, download y,
  * synchronise. *kernel_ms (optional) receives the CUDA-event time of the SpMV

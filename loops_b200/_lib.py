@@ -60,6 +60,19 @@ class PlanInfo(C.Structure):
     ]
 
 
+class TiledInfo(C.Structure):
+    """loopsb_tiled_info_t"""
+    _fields_ = [(n, C.c_int32) for n in ("nb", "q", "warps", "cb", "xb", "es", "rb", "rw", "cq", "nband",
+                                         "grid_blocks", "cta_threads", "smem_bytes", "reserved")] + \
+               [(n, C.c_int64) for n in ("total_steps", "real_entries", "pad_entries", "flagged_entries",
+                                         "flagged_steps", "bytes")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
+
+
+TILE_FORCE = 1
+
 # every symbol include/loopsb.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SIGNATURES = {
@@ -74,6 +87,14 @@ SIGNATURES = {
     "loopsb_plan_debug_phases_host": (C.c_int, [_P, _P, C.c_int64]),
     "loopsb_plan_probe_begin": (C.c_int, [_P, C.c_int32]),
     "loopsb_plan_probe_collect": (C.c_int, [_P, _P, C.c_int32, C.POINTER(C.c_int32)]),
+    "loopsb_plan_tile_csr": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "loopsb_plan_untile": (C.c_int, [_P]),
+    "loopsb_plan_tiled_info": (C.c_int, [_P, C.POINTER(TiledInfo)]),
+    "loopsb_tiled_image_build_host": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(C.c_int32 * 6),
+                                                C.POINTER(_P)]),
+    "loopsb_tiled_image_info": (C.c_int, [_P, C.POINTER(TiledInfo)]),
+    "loopsb_tiled_image_arrays": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "loopsb_tiled_image_free": (C.c_int, [_P]),
     "loopsb_spmv_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
     "loopsb_spmv_bcsr_f32": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(LayoutDesc), _P, _P, _P, _P, C.c_int32, _P]),
     "loopsb_spmv_bcsr4x4_bf16": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P]),

@@ -53,12 +53,12 @@ def _check_vec(name, t, n):
         raise ValueError(f"{name} must be a contiguous CUDA float32 tensor with >= {n} elements")
 
 
-def _run(container, schedule, values, cols, rows_idx, x, y, nrows, ncols, stream, sync, timed):
+def _run(container, schedule, values, cols, rows_idx, x, y, nrows, ncols, stream, sync, timed, tiled=None):
     lib = _lib.load()
     stream = stream or torch.cuda.current_stream()
     _check_vec("x", x, ncols)
     _check_vec("y", y, nrows)
-    plan = container.plan(schedule, stream)
+    plan = container.plan(schedule, stream, tiled) if isinstance(container, csr_t) else container.plan(schedule, stream)
     timer = timer_t(stream) if (timed and sync) else None
     if timer:
         timer.start()
@@ -72,12 +72,15 @@ def _run(container, schedule, values, cols, rows_idx, x, y, nrows, ncols, stream
     return timer
 
 
-def _csr(csr: csr_t, schedule, x, y, stream, sync, timed=False):
-    return _run(csr, schedule, csr.values, csr.indices, None, x, y, csr.rows, csr.cols, stream, sync, timed)
+def _csr(csr: csr_t, schedule, x, y, stream, sync, timed=False, tiled=None):
+    return _run(csr, schedule, csr.values, csr.indices, None, x, y, csr.rows, csr.cols, stream, sync, timed,
+                tiled)
 
 
-def merge_path_flat(csr: csr_t, x, y, stream=None, sync=True):
-    return _csr(csr, _lib.SCHED_MERGE_PATH_FLAT, x, y, stream, sync, timed=True)
+def merge_path_flat(csr: csr_t, x, y, stream=None, sync=True, tiled=None):
+    """``tiled``: see ``csr_t.plan`` (None = LOOPSB_TILED / cost model, True =
+    force the band-tiled kernel, False = the plain CSR merge-path kernel)."""
+    return _csr(csr, _lib.SCHED_MERGE_PATH_FLAT, x, y, stream, sync, timed=True, tiled=tiled)
 
 
 def work_oriented(csr: csr_t, x, y, stream=None, sync=True):

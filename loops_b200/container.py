@@ -66,6 +66,28 @@ class csr_t(_planned):
     def layout(self):
         return csr_layout(self.offsets, self.rows, self.nnzs)
 
+    def plan(self, schedule: int, stream=None, tiled=None):
+        """merge_path_flat plans may carry a band-tiled copy of the matrix
+        (``Plan.tile_csr``). ``tiled``: None = the LOOPSB_TILED environment
+        variable ("auto" by default: ask the library's cost model; "1" = force;
+        "0" = never), True = force, False = plain CSR kernel."""
+        import os
+        p = super().plan(schedule, stream)
+        if schedule != _lib.SCHED_MERGE_PATH_FLAT or not self.values.is_cuda or self.nnzs == 0:
+            return p
+        if tiled is None:
+            env = os.environ.get("LOOPSB_TILED", "auto")
+            tiled = {"0": False, "1": True}.get(env, "auto")
+        state = getattr(p, "_tile_state", None)
+        if tiled is False:
+            if state not in (None, "off"):
+                p.untile()
+            p._tile_state = "off"
+        elif state != ("forced" if tiled is True else "auto") and not (state == "forced" and tiled == "auto"):
+            p.tile_csr(self.indices, self.values, self.cols, force=(tiled is True), stream=stream)
+            p._tile_state = "forced" if tiled is True else "auto"
+        return p
+
     def host(self):
         return (self.offsets.cpu().numpy(), self.indices.cpu().numpy(), self.values.cpu().numpy())
 

@@ -6,6 +6,7 @@
 #include "spmv_merge.cuh"
 #include "spmv_schedules.cuh"
 #include "bcsr_tc.cuh"
+#include "spmv_tiled.cuh"
 
 #include <cstdarg>
 #include <cstdlib>
@@ -157,6 +158,8 @@ struct loopsb_plan {
   long long workspace_bytes = 0;
   // bcsr tensor-core path
   bcsr_tc::plan_data* tc = nullptr;
+  // band-tiled copy of a CSR matrix (loopsb_plan_tile_csr)
+  bt::plan_data* tiled = nullptr;
   // kernel-time probes (loopsb_plan_probe_*)
   cudaEvent_t* probe_ev = nullptr;  // 2 * probe_cap events
   int probe_cap = 0;
@@ -194,7 +197,194 @@ void free_probes(loopsb_plan* p) {
 }
 }  // namespace
 
+namespace {
+int launch_tiled(bt::plan_data* d, const float* x, float* y, cudaStream_t s) {
+  bt::params p;
+  p.steps = d->steps; p.stream_base = d->stream_base; p.fs = d->fs; p.le = d->le;
+  p.x = x; p.y = y; p.partial = d->partial; p.counters = d->counters;
+  p.rows = d->g.rows; p.cols = d->g.cols; p.rb = d->g.rb; p.cq = d->g.cq; p.cb = d->g.cb;
+  p.xb = d->g.xb; p.es = d->g.es; p.nband = d->g.nband; p.q = d->g.q; p.nb = d->g.nb;
+  bt::kernel_fn k = bt::kernel_for(d->g.warps);
+  k<<<d->g.grid(), d->g.cta_threads(), d->smem, s>>>(p);
+  LOOPSB_CUDA_TRY(cudaGetLastError());
+  return LOOPSB_OK;
+}
+
+void fill_tiled_info(loopsb_tiled_info_t* o, const bt::geom& g, long long total_steps, long long real_entries,
+                     long long pad_entries, long long flagged_entries, long long flagged_steps, long long bytes) {
+  memset(o, 0, sizeof(*o));
+  o->nb = g.nb; o->q = g.q; o->warps = g.warps; o->cb = g.cb; o->xb = g.xb; o->es = g.es;
+  o->rb = g.rb; o->rw = g.rw; o->cq = g.cq; o->nband = g.nband;
+  o->grid_blocks = g.grid(); o->cta_threads = g.cta_threads(); o->smem_bytes = g.smem_bytes();
+  o->total_steps = total_steps; o->real_entries = real_entries; o->pad_entries = pad_entries;
+  o->flagged_entries = flagged_entries; o->flagged_steps = flagged_steps; o->bytes = bytes;
+}
+}  // namespace
+
+struct loopsb_tiled_image {
+  bt::host_image im;
+};
+
 extern "C" {
+
+int loopsb_tiled_image_build_host(int32_t num_rows, int32_t num_cols, const int32_t* host_offsets,
+                                  const int32_t* host_indices, const float* host_values,
+                                  const int32_t geometry[6], loopsb_tiled_image_t** out) {
+  LOOPSB_REQUIRE(out != nullptr && geometry != nullptr && host_offsets != nullptr, "null argument");
+  *out = nullptr;
+  LOOPSB_REQUIRE(num_rows >= 0 && num_cols >= 0, "negative dimensions");
+  LOOPSB_REQUIRE(num_rows == 0 || host_offsets[num_rows] == 0 || (host_indices && host_values), "null matrix arrays");
+  loopsb_tiled_image* img = new (std::nothrow) loopsb_tiled_image();
+  if (!img) { set_error("host allocation failed"); return LOOPSB_ERR_ALLOC; }
+  bt::geom g;
+  g.nb = geometry[0]; g.q = geometry[1]; g.warps = geometry[2];
+  g.cb = geometry[3]; g.xb = geometry[4]; g.es = geometry[5];
+  int rc = LOOPSB_OK;
+  try {
+    rc = bt::build_host(img->im, g, num_rows, num_cols, host_offsets, host_indices, host_values);
+  } catch (const std::bad_alloc&) {
+    set_error("host allocation failed while tiling");
+    rc = LOOPSB_ERR_ALLOC;
+  }
+  if (rc != LOOPSB_OK) { delete img; return rc; }
+  *out = img;
+  return LOOPSB_OK;
+}
+
+int loopsb_tiled_image_info(const loopsb_tiled_image_t* img, loopsb_tiled_info_t* info) {
+  LOOPSB_REQUIRE(img != nullptr && info != nullptr, "null argument");
+  const bt::host_image& im = img->im;
+  fill_tiled_info(info, im.g, im.total_steps, im.real_entries, im.pad_entries, im.flagged_entries,
+                  im.flagged_steps, (long long)im.steps.size() * 4);
+  return LOOPSB_OK;
+}
+
+int loopsb_tiled_image_arrays(const loopsb_tiled_image_t* img, const uint32_t** steps,
+                              const int32_t** stream_base, const uint16_t** first_step,
+                              const uint16_t** last_step_end) {
+  LOOPSB_REQUIRE(img != nullptr, "null argument");
+  if (steps) *steps = img->im.steps.data();
+  if (stream_base) *stream_base = img->im.stream_base.data();
+  if (first_step) *first_step = img->im.fs.data();
+  if (last_step_end) *last_step_end = img->im.le.data();
+  return LOOPSB_OK;
+}
+
+int loopsb_tiled_image_free(loopsb_tiled_image_t* img) {
+  delete img;
+  return LOOPSB_OK;
+}
+
+int loopsb_plan_untile(loopsb_plan_t* plan) {
+  LOOPSB_REQUIRE(plan != nullptr, "plan is null");
+  if (plan->tiled) { bt::destroy(plan->tiled); plan->tiled = nullptr; }
+  return LOOPSB_OK;
+}
+
+int loopsb_plan_tiled_info(const loopsb_plan_t* plan, loopsb_tiled_info_t* info) {
+  LOOPSB_REQUIRE(plan != nullptr && info != nullptr, "null argument");
+  if (!plan->tiled) { set_error("the plan holds no band-tiled copy"); return LOOPSB_ERR_UNSUPPORTED; }
+  const bt::plan_data* d = plan->tiled;
+  fill_tiled_info(info, d->g, d->total_steps, d->real_entries, d->pad_entries, d->flagged_entries,
+                  d->flagged_steps, d->bytes);
+  return LOOPSB_OK;
+}
+
+int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const float* values,
+                         int32_t num_cols, int32_t flags, void* stream) {
+  LOOPSB_REQUIRE(plan != nullptr, "plan is null");
+  LOOPSB_REQUIRE(plan->schedule == LOOPSB_SCHED_MERGE_PATH_FLAT && plan->lay.kind == LOOPSB_LAYOUT_CSR,
+                 "band tiling applies to merge_path_flat plans over CSR");
+  LOOPSB_REQUIRE(num_cols >= 0, "negative columns");
+  const device_props* dp = current_device();
+  if (!dp) return LOOPSB_ERR_CUDA;
+  const int rows = plan->lay.num_tiles, nnz = plan->lay.num_atoms;
+  if (rows == 0 || nnz == 0 || num_cols == 0) { set_error("nothing to tile"); return LOOPSB_ERR_UNSUPPORTED; }
+  LOOPSB_REQUIRE(col_indices != nullptr && values != nullptr, "null matrix arrays");
+  cudaStream_t s = as_stream(stream);
+  const bool force = (flags & LOOPSB_TILE_FORCE) != 0;
+
+  bt::geom g = bt::choose_geom(rows, num_cols, dp->sm_count, dp->max_smem_optin);
+  const char* why = "";
+  if (!bt::derive(g, rows, num_cols, &why)) { set_error("band-tiled plan: %s", why); return LOOPSB_ERR_UNSUPPORTED; }
+  if (g.smem_bytes() > dp->max_smem_optin) {
+    set_error("band-tiled plan needs %d bytes of shared memory (device allows %d)", g.smem_bytes(), dp->max_smem_optin);
+    return LOOPSB_ERR_UNSUPPORTED;
+  }
+  if (!bt::kernel_for(g.warps)) { set_error("band-tiled plan: no kernel for %d consumer warps", g.warps); return LOOPSB_ERR_UNSUPPORTED; }
+  if (!force) {
+    // Cost model: every row block re-reads its column part of x from L2
+    // (nb * cols * 4 bytes in total) -- worth it only while that stays below
+    // the matrix stream itself, and only for matrices big enough to fill the chip.
+    const double x_traffic = double(g.nb) * double(num_cols) * 4.0;
+    const double stream_bytes = double(nnz) * 8.0;
+    if (nnz < (1 << 22) || x_traffic > stream_bytes) {
+      set_error("band-tiled plan not profitable (nnz %d, x re-read %.0f MB vs stream %.0f MB)", nnz,
+                x_traffic / 1e6, stream_bytes / 1e6);
+      return LOOPSB_ERR_UNSUPPORTED;
+    }
+  }
+
+  // The builder runs on the host (round 1): download CSR, tile, upload.
+  std::vector<int32_t> h_off, h_idx;
+  std::vector<float> h_val;
+  bt::host_image im;
+  int rc = LOOPSB_OK;
+  try {
+    h_off.resize(size_t(rows) + 1); h_idx.resize(size_t(nnz)); h_val.resize(size_t(nnz));
+    LOOPSB_CUDA_TRY(cudaStreamSynchronize(s));
+    LOOPSB_CUDA_TRY(cudaMemcpy(h_off.data(), plan->lay.offsets, h_off.size() * 4, cudaMemcpyDeviceToHost));
+    LOOPSB_CUDA_TRY(cudaMemcpy(h_idx.data(), col_indices, h_idx.size() * 4, cudaMemcpyDeviceToHost));
+    LOOPSB_CUDA_TRY(cudaMemcpy(h_val.data(), values, h_val.size() * 4, cudaMemcpyDeviceToHost));
+    LOOPSB_REQUIRE(h_off[rows] == nnz, "offsets[rows] must equal num_atoms");
+    rc = bt::build_host(im, g, rows, num_cols, h_off.data(), h_idx.data(), h_val.data());
+  } catch (const std::bad_alloc&) {
+    set_error("host allocation failed while tiling");
+    rc = LOOPSB_ERR_ALLOC;
+  }
+  if (rc != LOOPSB_OK) return rc;
+  h_idx.clear(); h_idx.shrink_to_fit(); h_val.clear(); h_val.shrink_to_fit();
+
+  bt::plan_data* d = new (std::nothrow) bt::plan_data();
+  if (!d) { set_error("host allocation failed"); return LOOPSB_ERR_ALLOC; }
+  d->g = im.g;
+  d->smem = im.g.smem_bytes();
+  auto fail = [&](int code) { bt::destroy(d); return code; };
+  const size_t steps_b = im.steps.size() * 4, base_b = im.stream_base.size() * 4;
+  const size_t tab_b = im.fs.size() * 2;
+  const size_t part_b = im.g.q > 1 ? size_t(im.g.q) * im.g.nb * im.g.rb * 4 : 0;
+  if (cudaMalloc(&d->steps, steps_b ? steps_b : 16) != cudaSuccess ||
+      cudaMalloc(&d->stream_base, base_b) != cudaSuccess ||
+      cudaMalloc(&d->fs, tab_b ? tab_b : 16) != cudaSuccess || cudaMalloc(&d->le, tab_b ? tab_b : 16) != cudaSuccess ||
+      (part_b && cudaMalloc(&d->partial, part_b) != cudaSuccess) ||
+      (part_b && cudaMalloc(&d->counters, size_t(im.g.nb) * 4) != cudaSuccess)) {
+    (void)cudaGetLastError();
+    set_error("device allocation of the band-tiled copy failed (%zu bytes)", steps_b + part_b);
+    return fail(LOOPSB_ERR_ALLOC);
+  }
+  if (cudaMemcpy(d->steps, im.steps.data(), steps_b, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(d->stream_base, im.stream_base.data(), base_b, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(d->fs, im.fs.data(), tab_b, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(d->le, im.le.data(), tab_b, cudaMemcpyHostToDevice) != cudaSuccess ||
+      (part_b && cudaMemset(d->counters, 0, size_t(im.g.nb) * 4) != cudaSuccess)) {
+    set_error("upload of the band-tiled copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(LOOPSB_ERR_CUDA);
+  }
+  bt::kernel_fn k = bt::kernel_for(im.g.warps);
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem) != cudaSuccess) {
+    set_error("cannot opt in to %d bytes of dynamic shared memory", d->smem);
+    (void)cudaGetLastError();
+    return fail(LOOPSB_ERR_CUDA);
+  }
+  d->key_indices = col_indices;
+  d->key_values = values;
+  d->total_steps = im.total_steps; d->real_entries = im.real_entries; d->pad_entries = im.pad_entries;
+  d->flagged_entries = im.flagged_entries; d->flagged_steps = im.flagged_steps;
+  d->bytes = (long long)(steps_b + base_b + 2 * tab_b + part_b + (part_b ? size_t(im.g.nb) * 4 : 0));
+  if (plan->tiled) bt::destroy(plan->tiled);
+  plan->tiled = d;
+  return LOOPSB_OK;
+}
 
 int loopsb_version(void) { return LOOPSB_VERSION; }
 
@@ -239,6 +429,7 @@ int loopsb_plan_destroy(loopsb_plan_t* plan) {
   if (plan->carry_val) cudaFree(plan->carry_val);
   if (plan->phases) cudaFree(plan->phases);
   if (plan->tc) bcsr_tc::destroy(plan->tc);
+  if (plan->tiled) bt::destroy(plan->tiled);
   free_probes(plan);
   delete plan;
   return LOOPSB_OK;
@@ -499,6 +690,13 @@ int loopsb_spmv_f32(loopsb_plan_t* plan, const float* values,
   switch (plan->schedule) {
     case LOOPSB_SCHED_MERGE_PATH_FLAT: {
       LOOPSB_REQUIRE(T == num_rows, "layout tiles must equal num_rows");
+      if (plan->tiled && plan->tiled->key_indices == col_indices && plan->tiled->key_values == values &&
+          plan->tiled->g.cols == num_cols && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+        probe_scope probe(plan, s);
+        int rc = launch_tiled(plan->tiled, x, y, s);
+        probe.close();
+        return rc;
+      }
       const int nct = plan->num_cta_tiles;
       probe_scope probe(plan, s);
       const merge_variant& mv = kMergeVariants[plan->variant];

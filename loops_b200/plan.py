@@ -35,6 +35,32 @@ class Plan:
                    "loopsb_plan_merge_coords_host")
         return out
 
+    def tile_csr(self, indices, values, cols: int, force: bool = False, stream=None) -> bool:
+        """Give the plan a band-tiled copy of the CSR matrix (``loopsb_plan_tile_csr``).
+        Returns False when the library declines (matrix does not fit the format
+        or the cost model prefers the plain kernel); the plan stays usable."""
+        rc = self._lib.loopsb_plan_tile_csr(self.handle, _lib.ptr(indices), _lib.ptr(values), int(cols),
+                                            _lib.TILE_FORCE if force else 0, _lib.stream_ptr(stream))
+        if rc == _lib.ERR_UNSUPPORTED:
+            self.tile_declined = self._lib.loopsb_last_error().decode(errors="replace")
+            return False
+        _lib.check(rc, "loopsb_plan_tile_csr")
+        self._tiled_keep = (indices, values)   # the copy is keyed by these pointers
+        return True
+
+    def untile(self):
+        _lib.check(self._lib.loopsb_plan_untile(self.handle), "loopsb_plan_untile")
+        self._tiled_keep = None
+
+    def tiled_info(self):
+        """dict of loopsb_tiled_info_t, or None when the plan holds no tiled copy."""
+        i = _lib.TiledInfo()
+        rc = self._lib.loopsb_plan_tiled_info(self.handle, C.byref(i))
+        if rc == _lib.ERR_UNSUPPORTED:
+            return None
+        _lib.check(rc, "loopsb_plan_tiled_info")
+        return i.as_dict()
+
     def probe_begin(self, capacity: int):
         """Bracket the dominant kernel of the next `capacity` SpMV calls with
         CUDA events (recorded on each call's stream)."""

@@ -1,0 +1,130 @@
+"""Host emulation of the band-tiled SpMV kernel (loops_b200/csrc/spmv_tiled.cuh)
+over the image the plan builder produces: walks every consumer warp's stream
+step by step with the kernel's acquire/release rules for the x ring, decodes
+every entry back to (row, col, value), and accumulates y in the kernel's order.
+It checks the format invariants the kernel relies on and raises AssertionError
+when one is broken. Test infrastructure only."""
+import ctypes as C
+
+import numpy as np
+
+FLAG = np.uint32(0x80000000)
+
+
+def build_image(lib, rows, cols, off, idx, val, geometry):
+    from loops_b200 import _lib
+    off = np.ascontiguousarray(off, np.int32)
+    idx = np.ascontiguousarray(idx, np.int32)
+    val = np.ascontiguousarray(val, np.float32)
+    geo = (C.c_int32 * 6)(*geometry)
+    h = C.c_void_p()
+    rc = lib.loopsb_tiled_image_build_host(rows, cols, off.ctypes.data, idx.ctypes.data if idx.size else None,
+                                           val.ctypes.data if val.size else None, C.byref(geo), C.byref(h))
+    if rc != 0:
+        return rc, None
+    info = _lib.TiledInfo()
+    assert lib.loopsb_tiled_image_info(h, C.byref(info)) == 0
+    ps = [C.c_void_p() for _ in range(4)]
+    assert lib.loopsb_tiled_image_arrays(h, *[C.byref(p) for p in ps]) == 0
+    g = info.as_dict()
+    ns = g["nb"] * g["q"] * g["warps"]
+
+    def arr(p, n, ct, dt):
+        if n == 0:
+            return np.zeros(0, dt)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), shape=(n,)).astype(dt, copy=True)
+
+    img = {
+        "g": g,
+        "steps": arr(ps[0], g["total_steps"] * 256, C.c_uint32, np.uint32).reshape(-1, 256),
+        "stream_base": arr(ps[1], ns + 1, C.c_int32, np.int64),
+        "fs": arr(ps[2], ns * g["nband"], C.c_uint16, np.int64).reshape(ns, g["nband"]),
+        "le": arr(ps[3], ns * g["nband"], C.c_uint16, np.int64).reshape(ns, g["nband"]),
+    }
+    lib.loopsb_tiled_image_free(h)
+    return 0, img
+
+
+def emulate(img, x, rows, cols):
+    """Returns (y, triples) where triples = sorted array of decoded (row, col, value bits)."""
+    g = img["g"]
+    nb, q, W, cb, xb = g["nb"], g["q"], g["warps"], g["cb"], g["xb"]
+    rb, rw, cq, nband = g["rb"], g["rw"], g["cq"], g["nband"]
+    zero_slot = xb * cb
+    partial = np.zeros((q, nb * rb), np.float32)
+    out_r, out_c, out_v = [], [], []
+    lane_of = np.repeat(np.arange(32), 4)
+    for cta in range(nb * q):
+        rbi, qi = divmod(cta, q)
+        ys = np.zeros(rb + 1, np.float32)
+        for w in range(W):
+            s_id = cta * W + w
+            base, end = img["stream_base"][s_id], img["stream_base"][s_id + 1]
+            fs, le = img["fs"][s_id], img["le"][s_id]
+            acq = rel = 0
+            resident = [-1] * xb
+            for s in range(end - base):
+                words = img["steps"][base + s]
+                ids, vals = words[:128], words[128:].view(np.float32)
+                while acq < nband and fs[acq] <= s:
+                    assert acq - rel < xb, ("x ring would deadlock", cta, w, s, acq, rel)
+                    resident[acq % xb] = acq
+                    acq += 1
+                    while rel < acq and le[rel] <= s:
+                        rel += 1
+                lc_enc = (ids & np.uint32(0xFFFF)).astype(np.int64)
+                lr = ((ids >> np.uint32(16)) & np.uint32(0x7FFF)).astype(np.int64)
+                flag = (ids & FLAG) != 0
+                pad = lr == rb
+                assert np.all(lc_enc[pad] == zero_slot) and np.all(vals[pad] == 0), "bad padding entry"
+                assert not np.any(flag[pad])
+                real = ~pad
+                assert np.all(lc_enc[real] < zero_slot)
+                k = lc_enc // cb
+                band = np.array([resident[int(kk)] if kk < xb else -1 for kk in k])
+                assert np.all(band[real] >= rel), ("entry of a released band", cta, w, s)
+                assert np.all(band[real] >= 0)
+                col = qi * cq + band * cb + (lc_enc - k * cb)
+                row = rbi * rb + lr
+                assert np.all(col[real] < cols) and np.all(row[real] < rows)
+                assert np.all((lr[real] // rw) == w), "row outside the warp's sub-block"
+                # collision flags: per slot j, unflagged lanes hold distinct rows;
+                # a flagged lane has an earlier lane with the same row
+                for j in range(4):
+                    sel = np.arange(j, 128, 4)
+                    seen = set()
+                    for i in sel:
+                        if pad[i]:
+                            continue
+                        r = int(lr[i])
+                        if flag[i]:
+                            assert r in seen, "flag without an earlier holder"
+                        else:
+                            assert r not in seen, ("unflagged collision", cta, w, s, j)
+                            seen.add(r)
+                # the kernel's arithmetic: unfused product, y updates in (j, lane) order
+                xv = np.where(real, x[np.where(real, col, 0)], np.float32(0)).astype(np.float32)
+                prod = (vals * xv).astype(np.float32)
+                for j in range(4):
+                    for i in range(j, 128, 4):
+                        ys[lr[i]] = np.float32(ys[lr[i]] + prod[i])
+                out_r.append(row[real]); out_c.append(col[real]); out_v.append(vals[real].view(np.uint32))
+                while rel < acq and le[rel] <= s + 1:
+                    rel += 1
+            nsteps = end - base
+            while acq < nband:
+                assert fs[acq] <= nsteps
+                assert acq - rel < xb
+                acq += 1
+                while rel < acq:
+                    assert le[rel] <= nsteps
+                    rel += 1
+            assert rel == acq == nband or nband == 0 or rel <= acq
+        partial[qi, rbi * rb: rbi * rb + rb] = ys[:rb]
+    y = partial[0].copy()
+    for qq in range(1, q):
+        y = (y + partial[qq]).astype(np.float32)
+    tr = np.stack([np.concatenate(out_r) if out_r else np.zeros(0, np.int64),
+                   np.concatenate(out_c) if out_c else np.zeros(0, np.int64),
+                   np.concatenate(out_v).astype(np.int64) if out_v else np.zeros(0, np.int64)], axis=1)
+    return y[:rows], tr
