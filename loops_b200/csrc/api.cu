@@ -204,7 +204,8 @@ int launch_tiled(bt::plan_data* d, const float* x, float* y, cudaStream_t s) {
   p.x = x; p.y = y; p.partial = d->partial; p.counters = d->counters;
   p.rows = d->g.rows; p.cols = d->g.cols; p.rb = d->g.rb; p.cq = d->g.cq; p.cb = d->g.cb;
   p.xb = d->g.xb; p.es = d->g.es; p.nband = d->g.nband; p.q = d->g.q; p.nb = d->g.nb;
-  bt::kernel_fn k = bt::kernel_for(d->g.warps);
+  p.prof = d->prof;
+  bt::kernel_fn k = bt::kernel_for(d->g.warps, d->prof != nullptr);
   k<<<d->g.grid(), d->g.cta_threads(), d->smem, s>>>(p);
   LOOPSB_CUDA_TRY(cudaGetLastError());
   return LOOPSB_OK;
@@ -352,7 +353,7 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const 
   auto fail = [&](int code) { bt::destroy(d); return code; };
   const size_t steps_b = im.steps.size() * 4, base_b = im.stream_base.size() * 4;
   const size_t tab_b = im.fs.size() * 2;
-  const size_t part_b = im.g.q > 1 ? size_t(im.g.q) * im.g.nb * im.g.rb * 4 : 0;
+  const size_t part_b = im.g.q > 1 ? size_t(im.g.q) * im.g.nb * ((im.g.rb + 3) & ~3) * 4 : 0;
   if (cudaMalloc(&d->steps, steps_b ? steps_b : 16) != cudaSuccess ||
       cudaMalloc(&d->stream_base, base_b) != cudaSuccess ||
       cudaMalloc(&d->fs, tab_b ? tab_b : 16) != cudaSuccess || cudaMalloc(&d->le, tab_b ? tab_b : 16) != cudaSuccess ||
@@ -370,7 +371,11 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const 
     set_error("upload of the band-tiled copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     return fail(LOOPSB_ERR_CUDA);
   }
-  bt::kernel_fn k = bt::kernel_for(im.g.warps);
+  if (getenv("LOOPSB_DEBUG_PHASES")) {
+    if (cudaMalloc(&d->prof, size_t(im.g.nstreams()) * 8 * sizeof(long long)) != cudaSuccess) { (void)cudaGetLastError(); d->prof = nullptr; }
+    else cudaMemset(d->prof, 0, size_t(im.g.nstreams()) * 8 * sizeof(long long));
+  }
+  bt::kernel_fn k = bt::kernel_for(im.g.warps, d->prof != nullptr);
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem) != cudaSuccess) {
     set_error("cannot opt in to %d bytes of dynamic shared memory", d->smem);
     (void)cudaGetLastError();
@@ -636,6 +641,13 @@ int loopsb_plan_merge_coords_host(const loopsb_plan_t* plan, int32_t* host_xy,
 int loopsb_plan_debug_phases_host(const loopsb_plan_t* plan, int64_t* host_out,
                                   int64_t capacity_ctas) {
   LOOPSB_REQUIRE(plan != nullptr && host_out != nullptr, "null argument");
+  if (plan->tiled && plan->tiled->prof) {   // band-tiled kernel: 8 counters per consumer warp
+    const long long n = plan->tiled->g.nstreams();
+    LOOPSB_REQUIRE(capacity_ctas >= n, "host buffer too small");
+    LOOPSB_CUDA_TRY(cudaDeviceSynchronize());
+    LOOPSB_CUDA_TRY(cudaMemcpy(host_out, plan->tiled->prof, size_t(n) * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return LOOPSB_OK;
+  }
   if (!plan->phases) { set_error("phase counters are off (set LOOPSB_DEBUG_PHASES=1 before creating the plan)"); return LOOPSB_ERR_UNSUPPORTED; }
   LOOPSB_REQUIRE(capacity_ctas >= plan->grid, "host buffer too small");
   LOOPSB_CUDA_TRY(cudaDeviceSynchronize());

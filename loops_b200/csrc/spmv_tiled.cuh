@@ -30,9 +30,9 @@
 // are one conflict-free 128-bit shared load and are consecutive in CSR order.
 //   id bits  0..15  position of x[col] in the x ring ((band % xb)*cb + col - band start)
 //      bits 16..30  row inside the CTA's row block
-//      bit  31      set when an earlier lane of the same step holds the same
-//                   row in the same slot j (the only way two lanes can collide
-//                   on a y row inside one instruction)
+//      bit  31      set on the entries of a row that the fast path cannot
+//                   combine inside the step (see "flags" in build_host); any
+//                   such entry sends the step down the general path
 // Padding entries have value 0, point at a zero word behind the x ring and at a
 // scratch row behind the y rows, so they need no predicate.
 // A step only holds bands of one window of `xb` consecutive bands (the plan
@@ -85,12 +85,13 @@ inline int ceil_div(long long a, long long b) { return int((a + b - 1) / b); }
 inline bool derive(geom& g, int rows, int cols, const char** why) {
   static const char* reasons[] = {"geometry fields must be positive", "cb must be a multiple of 4",
                                   "x ring exceeds 16 bits of position", "row block exceeds 15 bits of row",
-                                  "more than 31 consumer warps"};
+                                  "more than 31 consumer warps", "more than 8 column parts"};
   g.rows = rows; g.cols = cols;
   if (g.nb < 1 || g.q < 1 || g.warps < 1 || g.cb < 4 || g.xb < 2 || g.es < 2) { *why = reasons[0]; return false; }
   if (g.cb % 4) { *why = reasons[1]; return false; }
   if (g.xb * g.cb > kMaxRingFloats) { *why = reasons[2]; return false; }
   if (g.warps > 31) { *why = reasons[4]; return false; }
+  if (g.q > 8) { *why = reasons[5]; return false; }
   g.rb = std::max(1, ceil_div(rows, g.nb));
   if (g.rb > kMaxRowsPerBlock) { *why = reasons[3]; return false; }
   g.rw = std::max(1, ceil_div(g.rb, g.warps));
@@ -200,22 +201,33 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
   }
   im.real_entries = nnz;
   im.pad_entries = total * kStep - nnz;
-  // ---- pass 3: collision flags (same row, same slot j, earlier lane of the step) ----
-  std::vector<int64_t> seen(size_t(g.rb) + 1, -1);
-  for (long long s = 0; s < total; ++s) {
-    uint32_t* w = &im.steps[size_t(s) * kStepWords];
-    bool any = false;
-    for (int j = 0; j < kPerLane; ++j) {
-      const int64_t stamp = s * kPerLane + j;
-      for (int lane = 0; lane < kLanes; ++lane) {
-        uint32_t& id = w[lane * kPerLane + j];
-        const int lr = int((id >> 16) & 0x7fff);
+  // ---- pass 3: flags. A step is "clean" when every row it touches sits in ONE
+  // contiguous range of slots (slot = lane*4 + j, i.e. CSR order) that spans at
+  // most two adjacent lanes -- what the kernel's fast path can combine with a
+  // per-lane run sum and one neighbour shuffle. Entries of rows that break the
+  // rule (a row seen in two bands of the same step, or a run over 3+ lanes) get
+  // bit 31 and send the whole step down the general path. ----
+  {
+    std::vector<int64_t> stamp(size_t(g.rb) + 1, -1);
+    std::vector<int32_t> first(size_t(g.rb) + 1, 0), last(size_t(g.rb) + 1, 0), cnt(size_t(g.rb) + 1, 0);
+    for (long long s = 0; s < total; ++s) {
+      uint32_t* w = &im.steps[size_t(s) * kStepWords];
+      for (int p = 0; p < kStep; ++p) {
+        const int lr = int((w[p] >> 16) & 0x7fff);
         if (lr == g.rb) continue;  // padding -> scratch row, harmless
-        if (seen[lr] == stamp) { id |= kFlagBit; ++im.flagged_entries; any = true; }
-        else seen[lr] = stamp;
+        if (stamp[lr] != s) { stamp[lr] = s; first[lr] = last[lr] = p; cnt[lr] = 1; }
+        else { last[lr] = p; ++cnt[lr]; }
       }
+      bool any = false;
+      for (int p = 0; p < kStep; ++p) {
+        const int lr = int((w[p] >> 16) & 0x7fff);
+        if (lr == g.rb) continue;
+        const bool bad = (last[lr] - first[lr] + 1 != cnt[lr]) ||
+                         (last[lr] / kPerLane - first[lr] / kPerLane >= 2);
+        if (bad) { w[p] |= kFlagBit; ++im.flagged_entries; any = true; }
+      }
+      if (any) ++im.flagged_steps;
     }
-    if (any) ++im.flagged_steps;
   }
   return LOOPSB_OK;
 }
@@ -233,25 +245,27 @@ struct params {
   float* partial;       // [q][nb*rb] when q > 1
   unsigned* counters;   // [nb] when q > 1
   int rows, cols, rb, cq, cb, xb, es, nband, q, nb;
+  long long* prof;      // PROFILE builds: 8 counters per consumer warp
 };
 
-// One y update per flagged slot: lanes that are the first holder of their row
-// go first, the others follow one per round (rows compared with match.any).
-__device__ __forceinline__ void rmw_checked(float* ys, int r, float p, bool flagged) {
-  if (!flagged) ys[r] += p;
-  __syncwarp();
-  unsigned pend = __ballot_sync(0xffffffffu, flagged);
+// General y update for one slot of a dirty step: any lanes may hold the same
+// row. Lanes are grouped by row (match.any); the lowest lane of each group
+// updates, the rest retry, so equal rows are applied one after another in
+// lane order. Padding (scratch row) is skipped.
+__device__ __forceinline__ void rmw_general(float* ys, int r, float p, int scratch) {
+  bool todo = r != scratch;
+  unsigned pend = __ballot_sync(0xffffffffu, todo);
   while (pend) {
-    if (flagged) {
+    if (todo) {
       const unsigned grp = __match_any_sync(pend, r);
-      if ((__ffs(grp) - 1) == int(threadIdx.x & 31)) { ys[r] += p; flagged = false; }
+      if ((__ffs(grp) - 1) == int(threadIdx.x & 31)) { ys[r] += p; todo = false; }
     }
     __syncwarp();
-    pend = __ballot_sync(0xffffffffu, flagged);
+    pend = __ballot_sync(0xffffffffu, todo);
   }
 }
 
-template <int WARPS>
+template <int WARPS, bool PROFILE = false>
 __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const params p) {
   extern __shared__ __align__(16) unsigned char bt_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -333,67 +347,106 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
                                   stream_policy);
       }
     }
+    const uint32_t* refill = src + size_t(p.es) * kStepWords;  // next step to request
     const uint16_t* fsw = fs_s + warp * p.nband;
     const uint16_t* lew = le_s + warp * p.nband;
-    int acq = 0, rel = 0;
+    constexpr int kNever = 0x7fffffff;
+    // x-ring bookkeeping without divisions: slot and parity of the next band to
+    // acquire / release, and the step numbers at which that happens.
+    int acq = 0, rel = 0, acq_k = 0, rel_k = 0;
+    uint32_t acq_par = 0;
+    int nfs = p.nband > 0 ? int(fsw[0]) : kNever;  // first step that needs band `acq`
+    int nle = kNever;                              // band `rel` is finished once s + 1 >= nle
+    auto release_upto = [&](int limit) {           // release bands whose le <= limit
+      while (nle <= limit) {
+        if (lane == 0) loops::tma::barrier_arrive(&xempty[rel_k]);
+        ++rel;
+        if (++rel_k == p.xb) rel_k = 0;
+        nle = rel < acq ? int(lew[rel]) : kNever;
+      }
+    };
+    auto acquire_upto = [&](int s) {               // acquire every band first needed at step <= s
+      while (nfs <= s) {
+        loops::tma::barrier_wait(&xfull[acq_k], acq_par);
+        if (rel == acq) nle = int(lew[acq]);
+        ++acq;
+        if (++acq_k == p.xb) { acq_k = 0; acq_par ^= 1u; }
+        nfs = acq < p.nband ? int(fsw[acq]) : kNever;
+        release_upto(s);
+      }
+    };
     int st = 0;
     uint32_t ph = 0;
+    long long t_stream = 0, t_band = 0, t_gather = 0, t_fast = 0, t_slow = 0, n_slow = 0, t0 = 0, t1 = 0;
+    const long long t_begin = PROFILE ? clock64() : 0;
+    const int scratch = p.rb;
     for (int s = 0; s < nsteps; ++s) {
+      if (PROFILE) t0 = clock64();
       loops::tma::barrier_wait(&ef[st], ph);
-      const uint32_t* stage = ring + st * kStepWords;
+      if (PROFILE) { t1 = clock64(); t_stream += t1 - t0; t0 = t1; }
+      uint32_t* stage = ring + st * kStepWords;
       const uint4 I = reinterpret_cast<const uint4*>(stage)[lane];
       const float4 V = reinterpret_cast<const float4*>(stage + kStep)[lane];
-      // bands this step needs
-      while (acq < p.nband && int(fsw[acq]) <= s) {
-        loops::tma::barrier_wait(&xfull[acq % p.xb], uint32_t(acq / p.xb) & 1u);
-        ++acq;
-        while (rel < acq && int(lew[rel]) <= s) {
-          if (lane == 0) loops::tma::barrier_arrive(&xempty[rel % p.xb]);
-          ++rel;
-        }
-      }
+      acquire_upto(s);
+      if (PROFILE) { t1 = clock64(); t_band += t1 - t0; t0 = t1; }
       const float p0 = __fmul_rn(V.x, xs[I.x & 0xffffu]);
       const float p1 = __fmul_rn(V.y, xs[I.y & 0xffffu]);
       const float p2 = __fmul_rn(V.z, xs[I.z & 0xffffu]);
       const float p3 = __fmul_rn(V.w, xs[I.w & 0xffffu]);
       const int r0 = int((I.x >> 16) & 0x7fffu), r1 = int((I.y >> 16) & 0x7fffu);
       const int r2 = int((I.z >> 16) & 0x7fffu), r3 = int((I.w >> 16) & 0x7fffu);
-      __syncwarp();  // every lane has consumed its stage words and x values
+      const uint32_t fl = (I.x | I.y | I.z | I.w) & kFlagBit;
+      const bool dirty = __any_sync(0xffffffffu, fl != 0u);  // also: every lane is done with the stage
       if (lane == 0 && s + p.es < nsteps) {
         loops::tma::barrier_arrive_expect_tx(&ef[st], kStepWords * 4u);
-        loops::tma::bulk_g2s_hint(ring + st * kStepWords, src + size_t(s + p.es) * kStepWords, kStepWords * 4u,
-                                  &ef[st], stream_policy);
+        loops::tma::bulk_g2s_hint(stage, refill, kStepWords * 4u, &ef[st], stream_policy);
       }
-      const uint32_t fl = (I.x | I.y | I.z | I.w) & kFlagBit;
-      if (!__any_sync(0xffffffffu, fl != 0u)) {
-        ys[r0] += p0;
-        ys[r1] += p1;
-        ys[r2] += p2;
-        ys[r3] += p3;
+      refill += kStepWords;
+      if (PROFILE) { t1 = clock64(); t_gather += t1 - t0; t0 = t1; }
+      if (!dirty) {
+        // Clean step: a row's entries are one contiguous slot range over at most
+        // two adjacent lanes. Sum runs inside the lane, hand a run that started in
+        // the previous lane to that lane, then update distinct y rows independently.
+        const bool c1 = r1 == r0, c2 = r2 == r1, c3 = r3 == r2;
+        const float v0 = p0;
+        const float v1 = c1 ? v0 + p1 : p1;
+        const float v2 = c2 ? v1 + p2 : p2;
+        float v3 = c3 ? v2 + p3 : p3;
+        bool o0 = !c1, o1 = !c2, o2 = !c3, o3 = true;   // slot closes its run
+        const int prev_last = __shfl_up_sync(0xffffffffu, r3, 1);
+        const bool hc = lane > 0 && prev_last == r0;     // my first run continues the previous lane's last
+        const float hv = o0 ? v0 : (o1 ? v1 : (o2 ? v2 : v3));
+        float recv = __shfl_down_sync(0xffffffffu, hc ? hv : 0.f, 1);
+        if (lane == 31) recv = 0.f;
+        if (hc) {                                        // that run is written by the previous lane
+          if (o0) o0 = false; else if (o1) o1 = false; else if (o2) o2 = false; else o3 = false;
+        }
+        v3 += recv;
+        const float y0 = ys[o0 ? r0 : scratch], y1 = ys[o1 ? r1 : scratch];
+        const float y2 = ys[o2 ? r2 : scratch], y3 = ys[o3 ? r3 : scratch];
+        if (o0) ys[r0] = y0 + v0;
+        if (o1) ys[r1] = y1 + v1;
+        if (o2) ys[r2] = y2 + v2;
+        if (o3) ys[r3] = y3 + v3;
+        if (PROFILE) { t1 = clock64(); t_fast += t1 - t0; t0 = t1; }
       } else {
-        rmw_checked(ys, r0, p0, (I.x & kFlagBit) != 0u);
-        rmw_checked(ys, r1, p1, (I.y & kFlagBit) != 0u);
-        rmw_checked(ys, r2, p2, (I.z & kFlagBit) != 0u);
-        rmw_checked(ys, r3, p3, (I.w & kFlagBit) != 0u);
+        rmw_general(ys, r0, p0, scratch);
+        rmw_general(ys, r1, p1, scratch);
+        rmw_general(ys, r2, p2, scratch);
+        rmw_general(ys, r3, p3, scratch);
+        if (PROFILE) { t1 = clock64(); t_slow += t1 - t0; t0 = t1; ++n_slow; }
       }
-      while (rel < acq && int(lew[rel]) <= s + 1) {
-        if (lane == 0) loops::tma::barrier_arrive(&xempty[rel % p.xb]);
-        ++rel;
-      }
+      __syncwarp();   // y rows of this step are settled before the next step's loads
+      release_upto(s + 1);
       if (++st == p.es) { st = 0; ph ^= 1u; }
     }
     // bands after the warp's last step: keep the ring protocol going
-    while (acq < p.nband) {
-      loops::tma::barrier_wait(&xfull[acq % p.xb], uint32_t(acq / p.xb) & 1u);
-      ++acq;
-      while (rel < acq) {
-        if (lane == 0) loops::tma::barrier_arrive(&xempty[rel % p.xb]);
-        ++rel;
-      }
-    }
-    while (rel < acq) {
-      if (lane == 0) loops::tma::barrier_arrive(&xempty[rel % p.xb]);
-      ++rel;
+    acquire_upto(kNever - 1);
+    release_upto(kNever - 1);
+    if (PROFILE && lane == 0 && p.prof) {
+      long long* o = p.prof + size_t(ws) * 8;
+      o[0] = t_stream; o[1] = t_band; o[2] = t_gather; o[3] = t_fast; o[4] = t_slow; o[5] = n_slow;
+      o[6] = clock64() - t_begin; o[7] = nsteps;
     }
   }
   __syncthreads();
@@ -404,9 +457,15 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
     for (int i = tid; i < rows_here; i += NT) p.y[row0 + i] = ys[i];
     return;
   }
-  const size_t pitch = size_t(p.nb) * size_t(p.rb);
-  float* mine = p.partial + size_t(qi) * pitch + row0;
-  for (int i = tid; i < rows_here; i += NT) __stcg(mine + i, ys[i]);
+  // q > 1: publish this CTA's partial rows; the last of the q CTAs of the row
+  // block to arrive adds the partials in part order and writes y. Partials are
+  // padded to 4 rows per block so they move as 128-bit words.
+  const int rb4 = (p.rb + 3) & ~3;
+  const size_t pitch = size_t(p.nb) * size_t(rb4);
+  const int n4 = (rows_here + 3) >> 2;
+  float4* mine = reinterpret_cast<float4*>(p.partial + size_t(qi) * pitch + size_t(rbi) * rb4);
+  const float4* ys4 = reinterpret_cast<const float4*>(ys);
+  for (int i = tid; i < n4; i += NT) __stcg(mine + i, ys4[i]);
   __threadfence();
   __syncthreads();
   if (tid == 0) {
@@ -416,11 +475,26 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
   __syncthreads();
   if (*last_flag) {
     __threadfence();
-    for (int i = tid; i < rows_here; i += NT) {
-      float sum = (qi == 0) ? ys[i] : __ldcg(p.partial + row0 + i);
-      for (int qq = 1; qq < p.q; ++qq)
-        sum += (qq == qi) ? ys[i] : __ldcg(p.partial + size_t(qq) * pitch + row0 + i);
-      p.y[row0 + i] = sum;
+    const float4* part = reinterpret_cast<const float4*>(p.partial + size_t(rbi) * rb4);
+    const size_t pitch4 = pitch >> 2;
+    for (int i = tid; i < n4; i += NT) {
+      float4 v[8];
+#pragma unroll
+      for (int qq = 0; qq < 8; ++qq)
+        if (qq < p.q && qq != qi) v[qq] = __ldcg(part + size_t(qq) * pitch4 + i);
+      float4 acc = (qi == 0) ? ys4[i] : v[0];
+#pragma unroll
+      for (int qq = 1; qq < 8; ++qq)
+        if (qq < p.q) {
+          const float4 t = (qq == qi) ? ys4[i] : v[qq];
+          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+      const int r = 4 * i;
+      float* out = p.y + row0 + r;
+      out[0] = acc.x;
+      if (r + 1 < rows_here) out[1] = acc.y;
+      if (r + 2 < rows_here) out[2] = acc.z;
+      if (r + 3 < rows_here) out[3] = acc.w;
     }
     if (tid == 0) p.counters[rbi] = 0u;  // ready for the next launch
   }
@@ -442,24 +516,25 @@ struct plan_data {
   long long total_steps = 0, real_entries = 0, pad_entries = 0, flagged_entries = 0, flagged_steps = 0;
   long long bytes = 0;
   int smem = 0;
+  long long* prof = nullptr;  // LOOPSB_DEBUG_PHASES: 8 counters per consumer warp
 };
 
 inline void destroy(plan_data* d) {
   if (!d) return;
   cudaFree(d->steps); cudaFree(d->stream_base); cudaFree(d->fs); cudaFree(d->le);
-  cudaFree(d->partial); cudaFree(d->counters);
+  cudaFree(d->partial); cudaFree(d->counters); cudaFree(d->prof);
   delete d;
 }
 
 using kernel_fn = void (*)(const params);
-inline kernel_fn kernel_for(int warps) {
+inline kernel_fn kernel_for(int warps, bool profile = false) {
   switch (warps) {
-    case 4: return spmv_bt_kernel<4>;
-    case 8: return spmv_bt_kernel<8>;
-    case 12: return spmv_bt_kernel<12>;
-    case 16: return spmv_bt_kernel<16>;
-    case 20: return spmv_bt_kernel<20>;
-    case 24: return spmv_bt_kernel<24>;
+    case 4: return profile ? spmv_bt_kernel<4, true> : spmv_bt_kernel<4>;
+    case 8: return profile ? spmv_bt_kernel<8, true> : spmv_bt_kernel<8>;
+    case 12: return profile ? spmv_bt_kernel<12, true> : spmv_bt_kernel<12>;
+    case 16: return profile ? spmv_bt_kernel<16, true> : spmv_bt_kernel<16>;
+    case 20: return profile ? spmv_bt_kernel<20, true> : spmv_bt_kernel<20>;
+    case 24: return profile ? spmv_bt_kernel<24, true> : spmv_bt_kernel<24>;
     default: return nullptr;
   }
 }
@@ -471,8 +546,8 @@ inline geom choose_geom(int rows, int cols, int sms, int max_smem) {
   geom g;
   g.q = (sms % 4 == 0) ? 4 : (sms % 2 == 0 ? 2 : 1);
   g.warps = 16;
-  g.xb = 2;
-  g.es = 3;
+  g.xb = 4;
+  g.es = 2;
   int over[6] = {0, 0, 0, 0, 0, 0};
   if (const char* e = getenv("LOOPSB_TILED_GEOM"))
     sscanf(e, "%d,%d,%d,%d,%d,%d", &over[0], &over[1], &over[2], &over[3], &over[4], &over[5]);
@@ -496,9 +571,9 @@ inline geom choose_geom(int rows, int cols, int sms, int max_smem) {
   if (over[3] > 0) {
     g.cb = over[3];
   } else {
-    // widest band (<= 8192 columns) whose ring still fits beside y and the stream rings
+    // widest band (<= 4096 columns) whose ring still fits beside y and the stream rings
     const int cq = std::max(4, (ceil_div(cols, g.q) + 3) & ~3);
-    int cb = std::min(std::min(kMaxRingFloats / g.xb, 8192), (cq + 63) & ~63) & ~3;
+    int cb = std::min(std::min(kMaxRingFloats / g.xb, 4096), (cq + 63) & ~63) & ~3;
     for (; cb > 64; cb -= 64) {
       geom t = g;
       t.cb = cb;

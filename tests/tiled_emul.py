@@ -88,26 +88,47 @@ def emulate(img, x, rows, cols):
                 row = rbi * rb + lr
                 assert np.all(col[real] < cols) and np.all(row[real] < rows)
                 assert np.all((lr[real] // rw) == w), "row outside the warp's sub-block"
-                # collision flags: per slot j, unflagged lanes hold distinct rows;
-                # a flagged lane has an earlier lane with the same row
-                for j in range(4):
-                    sel = np.arange(j, 128, 4)
-                    seen = set()
-                    for i in sel:
-                        if pad[i]:
-                            continue
-                        r = int(lr[i])
-                        if flag[i]:
-                            assert r in seen, "flag without an earlier holder"
-                        else:
-                            assert r not in seen, ("unflagged collision", cta, w, s, j)
-                            seen.add(r)
-                # the kernel's arithmetic: unfused product, y updates in (j, lane) order
                 xv = np.where(real, x[np.where(real, col, 0)], np.float32(0)).astype(np.float32)
                 prod = (vals * xv).astype(np.float32)
-                for j in range(4):
-                    for i in range(j, 128, 4):
-                        ys[lr[i]] = np.float32(ys[lr[i]] + prod[i])
+                # rows that the fast path cannot combine: not one contiguous slot
+                # range, or a range over three or more lanes
+                slots_of = {}
+                for i in range(128):
+                    if not pad[i]:
+                        slots_of.setdefault(int(lr[i]), []).append(i)
+                bad_rows = {r for r, sl in slots_of.items()
+                            if sl[-1] - sl[0] + 1 != len(sl) or sl[-1] // 4 - sl[0] // 4 >= 2}
+                for i in range(128):
+                    if not pad[i]:
+                        assert bool(flag[i]) == (int(lr[i]) in bad_rows), ("flag mismatch", cta, w, s, i)
+                if not flag.any():
+                    # clean step, the kernel's order: run sums inside a lane, a run that
+                    # started in the previous lane is handed to it, one update per run
+                    v = prod.copy()
+                    for i in range(128):
+                        if i % 4 and lr[i] == lr[i - 1]:
+                            v[i] = np.float32(v[i - 1] + prod[i])
+                    send = np.zeros(32, np.float32)
+                    own = np.ones(128, bool)
+                    for i in range(128):
+                        if i % 4 != 3 and lr[i + 1] == lr[i]:
+                            own[i] = False
+                    for lane in range(1, 32):
+                        if lr[4 * lane] == lr[4 * lane - 1]:
+                            h = next(i for i in range(4 * lane, 4 * lane + 4) if own[i])
+                            send[lane] = v[h]
+                            own[h] = False
+                    for lane in range(31):
+                        v[4 * lane + 3] = np.float32(v[4 * lane + 3] + send[lane + 1])
+                    for i in range(128):
+                        if own[i]:
+                            ys[lr[i]] = np.float32(ys[lr[i]] + v[i])
+                else:
+                    # dirty step: slot by slot, equal rows applied in lane order
+                    for j in range(4):
+                        for i in range(j, 128, 4):
+                            if not pad[i]:
+                                ys[lr[i]] = np.float32(ys[lr[i]] + prod[i])
                 out_r.append(row[real]); out_c.append(col[real]); out_v.append(vals[real].view(np.uint32))
                 while rel < acq and le[rel] <= s + 1:
                     rel += 1
