@@ -69,6 +69,23 @@ __device__ __forceinline__ void barrier_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+/// Same, but each failed probe lets the hardware park the thread (suspend-time
+/// hint, in ns) instead of spinning: waiting warps stop competing for issue
+/// slots with the warps that still have work.
+__device__ __forceinline__ void barrier_wait_suspend(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAITS_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONES_%=;\n"
+      "bra WAITS_%=;\n"
+      "DONES_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+
 /// 1-D bulk copy global -> shared::cta, completion on `bar`.
 /// `bytes` % 16 == 0, both addresses 16-byte aligned, bytes > 0.
 __device__ __forceinline__ void bulk_g2s(void* smem_dst,

@@ -194,7 +194,7 @@ int loopsb_spmv_bcsr4x4_bf16(loopsb_plan_t* plan, const uint16_t* values_bf16,
 typedef struct loopsb_tiled_info {
   int32_t nb, q, warps, cb, xb, es;   /* row blocks, column parts, consumer warps,
                                          band width, x-ring depth, stream-ring depth */
-  int32_t rb, rw, cq, nband;          /* rows/block, rows/warp, columns/part, bands/part */
+  int32_t rb, rw, cq, nband;          /* max rows/block, max rows/warp, columns/part, bands/part */
   int32_t grid_blocks, cta_threads, smem_bytes, reserved;
   int64_t total_steps;                /* 1 KB steps (128 entries) in the copy   */
   int64_t real_entries, pad_entries;  /* nnz and padding entries                */
@@ -219,9 +219,13 @@ int loopsb_tiled_image_build_host(int32_t num_rows, int32_t num_cols,
                                   const int32_t geometry[6],
                                   loopsb_tiled_image_t** out);
 int loopsb_tiled_image_info(const loopsb_tiled_image_t* img, loopsb_tiled_info_t* info);
+/* steps[total_steps*256], stream_base[nb*q*warps+1], first_step / last_step_end
+ * [nb*q*warps][nband], block_begin[nb+1] (row-block cuts, by nonzero count),
+ * warp_begin[nb*q][warps+1] (block-local row cuts between consumer warps). */
 int loopsb_tiled_image_arrays(const loopsb_tiled_image_t* img, const uint32_t** steps,
                               const int32_t** stream_base, const uint16_t** first_step,
-                              const uint16_t** last_step_end);
+                              const uint16_t** last_step_end, const int32_t** block_begin,
+                              const int32_t** warp_begin);
 int loopsb_tiled_image_free(loopsb_tiled_image_t* img);
 
 /* Host-buffer convenience with the flow of the reference's example mains

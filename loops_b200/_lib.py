@@ -93,7 +93,7 @@ SIGNATURES = {
     "loopsb_tiled_image_build_host": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(C.c_int32 * 6),
                                                 C.POINTER(_P)]),
     "loopsb_tiled_image_info": (C.c_int, [_P, C.POINTER(TiledInfo)]),
-    "loopsb_tiled_image_arrays": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "loopsb_tiled_image_arrays": (C.c_int, [_P] + [C.POINTER(_P)] * 6),
     "loopsb_tiled_image_free": (C.c_int, [_P]),
     "loopsb_spmv_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
     "loopsb_spmv_bcsr_f32": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(LayoutDesc), _P, _P, _P, _P, C.c_int32, _P]),

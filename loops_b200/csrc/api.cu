@@ -200,12 +200,12 @@ void free_probes(loopsb_plan* p) {
 namespace {
 int launch_tiled(bt::plan_data* d, const float* x, float* y, cudaStream_t s) {
   bt::params p;
-  p.steps = d->steps; p.stream_base = d->stream_base; p.fs = d->fs; p.le = d->le;
+  p.steps = d->steps; p.stream_base = d->stream_base; p.blk_begin = d->blk_begin; p.fs = d->fs; p.le = d->le;
   p.x = x; p.y = y; p.partial = d->partial; p.counters = d->counters;
   p.rows = d->g.rows; p.cols = d->g.cols; p.rb = d->g.rb; p.cq = d->g.cq; p.cb = d->g.cb;
   p.xb = d->g.xb; p.es = d->g.es; p.nband = d->g.nband; p.q = d->g.q; p.nb = d->g.nb;
   p.prof = d->prof;
-  bt::kernel_fn k = bt::kernel_for(d->g.warps, d->prof != nullptr);
+  bt::kernel_fn k = bt::kernel_for(d->g.warps, d->g.es, d->prof != nullptr);
   k<<<d->g.grid(), d->g.cta_threads(), d->smem, s>>>(p);
   LOOPSB_CUDA_TRY(cudaGetLastError());
   return LOOPSB_OK;
@@ -262,8 +262,11 @@ int loopsb_tiled_image_info(const loopsb_tiled_image_t* img, loopsb_tiled_info_t
 
 int loopsb_tiled_image_arrays(const loopsb_tiled_image_t* img, const uint32_t** steps,
                               const int32_t** stream_base, const uint16_t** first_step,
-                              const uint16_t** last_step_end) {
+                              const uint16_t** last_step_end, const int32_t** block_begin,
+                              const int32_t** warp_begin) {
   LOOPSB_REQUIRE(img != nullptr, "null argument");
+  if (block_begin) *block_begin = img->im.blk_begin.data();
+  if (warp_begin) *warp_begin = img->im.warp_begin.data();
   if (steps) *steps = img->im.steps.data();
   if (stream_base) *stream_base = img->im.stream_base.data();
   if (first_step) *first_step = img->im.fs.data();
@@ -312,7 +315,10 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const 
     set_error("band-tiled plan needs %d bytes of shared memory (device allows %d)", g.smem_bytes(), dp->max_smem_optin);
     return LOOPSB_ERR_UNSUPPORTED;
   }
-  if (!bt::kernel_for(g.warps)) { set_error("band-tiled plan: no kernel for %d consumer warps", g.warps); return LOOPSB_ERR_UNSUPPORTED; }
+  if (!bt::kernel_for(g.warps, g.es)) {
+    set_error("band-tiled plan: no kernel for %d consumer warps / prefetch depth %d", g.warps, g.es);
+    return LOOPSB_ERR_UNSUPPORTED;
+  }
   if (!force) {
     // Cost model: every row block re-reads its column part of x from L2
     // (nb * cols * 4 bytes in total) -- worth it only while that stays below
@@ -356,6 +362,7 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const 
   const size_t part_b = im.g.q > 1 ? size_t(im.g.q) * im.g.nb * ((im.g.rb + 3) & ~3) * 4 : 0;
   if (cudaMalloc(&d->steps, steps_b ? steps_b : 16) != cudaSuccess ||
       cudaMalloc(&d->stream_base, base_b) != cudaSuccess ||
+      cudaMalloc(&d->blk_begin, im.blk_begin.size() * 4) != cudaSuccess ||
       cudaMalloc(&d->fs, tab_b ? tab_b : 16) != cudaSuccess || cudaMalloc(&d->le, tab_b ? tab_b : 16) != cudaSuccess ||
       (part_b && cudaMalloc(&d->partial, part_b) != cudaSuccess) ||
       (part_b && cudaMalloc(&d->counters, size_t(im.g.nb) * 4) != cudaSuccess)) {
@@ -365,6 +372,7 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const 
   }
   if (cudaMemcpy(d->steps, im.steps.data(), steps_b, cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(d->stream_base, im.stream_base.data(), base_b, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(d->blk_begin, im.blk_begin.data(), im.blk_begin.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(d->fs, im.fs.data(), tab_b, cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(d->le, im.le.data(), tab_b, cudaMemcpyHostToDevice) != cudaSuccess ||
       (part_b && cudaMemset(d->counters, 0, size_t(im.g.nb) * 4) != cudaSuccess)) {
@@ -372,10 +380,10 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const 
     return fail(LOOPSB_ERR_CUDA);
   }
   if (getenv("LOOPSB_DEBUG_PHASES")) {
-    if (cudaMalloc(&d->prof, size_t(im.g.nstreams()) * 8 * sizeof(long long)) != cudaSuccess) { (void)cudaGetLastError(); d->prof = nullptr; }
-    else cudaMemset(d->prof, 0, size_t(im.g.nstreams()) * 8 * sizeof(long long));
+    if (cudaMalloc(&d->prof, (size_t(im.g.nstreams()) * 8 + size_t(im.g.grid()) * 4) * sizeof(long long)) != cudaSuccess) { (void)cudaGetLastError(); d->prof = nullptr; }
+    else cudaMemset(d->prof, 0, (size_t(im.g.nstreams()) * 8 + size_t(im.g.grid()) * 4) * sizeof(long long));
   }
-  bt::kernel_fn k = bt::kernel_for(im.g.warps, d->prof != nullptr);
+  bt::kernel_fn k = bt::kernel_for(im.g.warps, im.g.es, d->prof != nullptr);
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem) != cudaSuccess) {
     set_error("cannot opt in to %d bytes of dynamic shared memory", d->smem);
     (void)cudaGetLastError();
@@ -642,10 +650,13 @@ int loopsb_plan_debug_phases_host(const loopsb_plan_t* plan, int64_t* host_out,
                                   int64_t capacity_ctas) {
   LOOPSB_REQUIRE(plan != nullptr && host_out != nullptr, "null argument");
   if (plan->tiled && plan->tiled->prof) {   // band-tiled kernel: 8 counters per consumer warp
+    // 8 counters per consumer warp, then (if the buffer has room) 4 wall-clock stamps per CTA
     const long long n = plan->tiled->g.nstreams();
+    const long long extra = (plan->tiled->g.grid() * 4 + 7) / 8;
     LOOPSB_REQUIRE(capacity_ctas >= n, "host buffer too small");
+    const long long take = capacity_ctas >= n + extra ? n * 8 + plan->tiled->g.grid() * 4 : n * 8;
     LOOPSB_CUDA_TRY(cudaDeviceSynchronize());
-    LOOPSB_CUDA_TRY(cudaMemcpy(host_out, plan->tiled->prof, size_t(n) * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    LOOPSB_CUDA_TRY(cudaMemcpy(host_out, plan->tiled->prof, size_t(take) * sizeof(long long), cudaMemcpyDeviceToHost));
     return LOOPSB_OK;
   }
   if (!plan->phases) { set_error("phase counters are off (set LOOPSB_DEBUG_PHASES=1 before creating the plan)"); return LOOPSB_ERR_UNSUPPORTED; }

@@ -69,12 +69,12 @@ struct geom {
   int cta_threads() const { return (warps + 1) * 32; }
   int zero_slot() const { return xb * cb; }
   // shared-memory carve-up (bytes), identical in the kernel
-  int bar_count() const { return (2 * xb + warps * es + 1) & ~1; }
+  int bar_count() const { return (2 * xb + 1) & ~1; }
   int ys_words() const { return (rb + 1 + 3) & ~3; }
   int xs_words() const { return xb * cb + 4; }
   int table_bytes() const { return ((2 * warps * nband * 2 + 4) + 15) & ~15; }
   int smem_bytes() const {
-    return bar_count() * 8 + warps * es * kStepWords * 4 + xs_words() * 4 + ys_words() * 4 + table_bytes();
+    return bar_count() * 8 + xs_words() * 4 + ys_words() * 4 + table_bytes();
   }
 };
 
@@ -92,8 +92,12 @@ inline bool derive(geom& g, int rows, int cols, const char** why) {
   if (g.xb * g.cb > kMaxRingFloats) { *why = reasons[2]; return false; }
   if (g.warps > 31) { *why = reasons[4]; return false; }
   if (g.q > 8) { *why = reasons[5]; return false; }
-  g.rb = std::max(1, ceil_div(rows, g.nb));
-  if (g.rb > kMaxRowsPerBlock) { *why = reasons[3]; return false; }
+  // rb is an UPPER BOUND here (row blocks are cut by nonzero count, so a block
+  // of light rows may hold up to ~15 % more rows than rows/nb); build_host
+  // replaces it by the largest block actually cut.
+  const int even = std::max(1, ceil_div(rows, g.nb));
+  if (even > kMaxRowsPerBlock) { *why = reasons[3]; return false; }
+  g.rb = std::min(kMaxRowsPerBlock, even + even / 7 + 8);
   g.rw = std::max(1, ceil_div(g.rb, g.warps));
   g.cq = std::max(4, (ceil_div(cols, g.q) + 3) & ~3);
   g.nband = std::max(1, ceil_div(g.cq, g.cb));
@@ -107,6 +111,8 @@ struct host_image {
   std::vector<int32_t> stream_base;  // nstreams + 1, in steps
   std::vector<uint16_t> fs;          // [stream][band] first step holding the band
   std::vector<uint16_t> le;          // [stream][band] one past the last step holding it
+  std::vector<int32_t> blk_begin;    // nb + 1: first row of every row block (cut by nonzero count)
+  std::vector<int32_t> warp_begin;   // [cta][warps + 1]: block-local first row of every consumer warp
   long long total_steps = 0, real_entries = 0, pad_entries = 0, flagged_entries = 0, flagged_steps = 0;
 };
 
@@ -116,19 +122,74 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
                       const float* val) {
   const char* why = "";
   if (!derive(g, rows, cols, &why)) { set_error("band-tiled plan: %s", why); return LOOPSB_ERR_UNSUPPORTED; }
-  im.g = g;
   const int ns = g.nstreams(), nband = g.nband;
   const long long nnz = rows > 0 ? off[rows] : 0;
-  std::vector<int32_t> count(size_t(ns) * nband, 0);
-  // ---- pass 1: entries per (stream, band) ----
-  for (int r = 0; r < rows; ++r) {
-    const int rbi = r / g.rb, lr = r - rbi * g.rb, w = lr / g.rw;
-    const size_t sb = size_t(rbi) * g.q;
+  // ---- pass 0: nonzeros per (row, column part); validates the column ids ----
+  std::vector<int32_t> rowpart(size_t(rows) * g.q, 0);
+  for (int r = 0; r < rows; ++r)
     for (int a = off[r]; a < off[r + 1]; ++a) {
       const int c = idx[a];
       if (c < 0 || c >= cols) { set_error("band-tiled plan: column id %d out of range at atom %d", c, a); return LOOPSB_ERR_INVALID; }
-      const int qi = c / g.cq, cl = c - qi * g.cq, b = cl / g.cb;
-      ++count[((sb + qi) * g.warps + w) * nband + b];
+      ++rowpart[size_t(r) * g.q + c / g.cq];
+    }
+  // ---- row blocks: equal nonzero counts, at most g.rb rows each ----
+  const int rb_cap = g.rb;
+  im.blk_begin.assign(size_t(g.nb) + 1, 0);
+  {
+    int prev = 0;
+    for (int k = 1; k <= g.nb; ++k) {
+      const long long target = nnz * k / g.nb;
+      int cut = int(std::lower_bound(off, off + rows + 1, target) - off);   // first row r with off[r] >= target
+      const long long lo = std::max<long long>(prev, (long long)rows - (long long)(g.nb - k) * rb_cap);
+      const long long hi = std::min<long long>(rows, (long long)prev + rb_cap);
+      cut = int(std::min<long long>(std::max<long long>(cut, lo), hi));
+      if (k == g.nb) cut = rows;
+      im.blk_begin[k] = cut;
+      prev = cut;
+    }
+  }
+  int rb_max = 1;
+  for (int k = 0; k < g.nb; ++k) rb_max = std::max(rb_max, im.blk_begin[k + 1] - im.blk_begin[k]);
+  g.rb = rb_max;
+  // ---- consumer warps: contiguous row ranges of the block with equal nonzero
+  // counts inside this CTA's column part ----
+  im.warp_begin.assign(size_t(g.grid()) * (g.warps + 1), 0);
+  std::vector<uint8_t> wmap(size_t(rows) * g.q, 0);   // warp that owns (row, part)
+  int rw_max = 1;
+  for (int rbi = 0; rbi < g.nb; ++rbi) {
+    const int b0 = im.blk_begin[rbi], b1 = im.blk_begin[rbi + 1];
+    for (int qi = 0; qi < g.q; ++qi) {
+      long long tot = 0;
+      for (int r = b0; r < b1; ++r) tot += rowpart[size_t(r) * g.q + qi];
+      int32_t* wb = &im.warp_begin[(size_t(rbi) * g.q + qi) * (g.warps + 1)];
+      long long acc = 0;
+      int w = 0;
+      wb[0] = 0;
+      for (int r = b0; r < b1; ++r) {
+        // row r opens warp w+1 once the rows before it hold w+1 shares of the nonzeros
+        while (w + 1 < g.warps && acc * g.warps >= tot * (w + 1) && tot > 0) wb[++w] = r - b0;
+        wmap[size_t(r) * g.q + qi] = uint8_t(w);
+        acc += rowpart[size_t(r) * g.q + qi];
+      }
+      while (w + 1 <= g.warps) wb[++w] = b1 - b0;
+      for (int k = 0; k < g.warps; ++k) rw_max = std::max(rw_max, wb[k + 1] - wb[k]);
+    }
+  }
+  g.rw = rw_max;
+  im.g = g;
+  std::vector<int32_t> count(size_t(ns) * nband, 0);
+  // ---- pass 1: entries per (stream, band) ----
+  {
+    int rbi = 0;
+    for (int r = 0; r < rows; ++r) {
+      while (r >= im.blk_begin[rbi + 1]) ++rbi;
+      const size_t sb = size_t(rbi) * g.q;
+      for (int a = off[r]; a < off[r + 1]; ++a) {
+        const int c = idx[a];
+        const int qi = c / g.cq, cl = c - qi * g.cq, b = cl / g.cb;
+        const int w = wmap[size_t(r) * g.q + qi];
+        ++count[((sb + qi) * g.warps + w) * nband + b];
+      }
     }
   }
   // ---- layout: padded start of every band in every stream ----
@@ -183,20 +244,24 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
     for (int i = 0; i < kStep; ++i) w[i] = pad_id;
   }
   std::vector<int32_t>& cursor = start;  // consumed in place
-  for (int r = 0; r < rows; ++r) {
-    const int rbi = r / g.rb, lr = r - rbi * g.rb, w = lr / g.rw;
-    const size_t sb = size_t(rbi) * g.q;
-    for (int a = off[r]; a < off[r + 1]; ++a) {
-      const int c = idx[a];
-      const int qi = c / g.cq, cl = c - qi * g.cq, b = cl / g.cb, lc = cl - b * g.cb;
-      const size_t stream = (sb + qi) * g.warps + w;
-      const int32_t p = cursor[stream * nband + b]++;
-      uint32_t* sw = &im.steps[(size_t(im.stream_base[stream]) + size_t(p / kStep)) * kStepWords];
-      const int slot = p % kStep;  // lane*4 + j
-      sw[slot] = (uint32_t(lr) << 16) | uint32_t((b % g.xb) * g.cb + lc);
-      float v = val[a];
-      uint32_t vb; memcpy(&vb, &v, 4);
-      sw[kStep + slot] = vb;
+  {
+    int rbi = 0;
+    for (int r = 0; r < rows; ++r) {
+      while (r >= im.blk_begin[rbi + 1]) ++rbi;
+      const int lr = r - im.blk_begin[rbi];
+      const size_t sb = size_t(rbi) * g.q;
+      for (int a = off[r]; a < off[r + 1]; ++a) {
+        const int c = idx[a];
+        const int qi = c / g.cq, cl = c - qi * g.cq, b = cl / g.cb, lc = cl - b * g.cb;
+        const size_t stream = (sb + qi) * g.warps + wmap[size_t(r) * g.q + qi];
+        const int32_t p = cursor[stream * nband + b]++;
+        uint32_t* sw = &im.steps[(size_t(im.stream_base[stream]) + size_t(p / kStep)) * kStepWords];
+        const int slot = p % kStep;  // lane*4 + j
+        sw[slot] = (uint32_t(lr) << 16) | uint32_t((b % g.xb) * g.cb + lc);
+        float v = val[a];
+        uint32_t vb; memcpy(&vb, &v, 4);
+        sw[kStep + slot] = vb;
+      }
     }
   }
   im.real_entries = nnz;
@@ -238,6 +303,7 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
 struct params {
   const uint32_t* steps;
   const int32_t* stream_base;
+  const int32_t* blk_begin;   // nb + 1 row-block boundaries
   const uint16_t* fs;
   const uint16_t* le;
   const float* x;
@@ -245,7 +311,7 @@ struct params {
   float* partial;       // [q][nb*rb] when q > 1
   unsigned* counters;   // [nb] when q > 1
   int rows, cols, rb, cq, cb, xb, es, nband, q, nb;
-  long long* prof;      // PROFILE builds: 8 counters per consumer warp
+  long long* prof;      // PROFILE builds: 8 counters per consumer warp, then 4 wall-clock stamps per CTA
 };
 
 // General y update for one slot of a dirty step: any lanes may hold the same
@@ -265,23 +331,37 @@ __device__ __forceinline__ void rmw_general(float* ys, int r, float p, int scrat
   }
 }
 
-template <int WARPS, bool PROFILE = false>
+// One 1 KB step of a warp's stream, held in registers: ids and values of the
+// lane's four entries. Loaded straight from HBM with two coalesced 128-bit
+// streaming loads per lane, DEPTH steps ahead of their use.
+struct step_regs {
+  uint4 I;
+  float4 V;
+};
+
+__device__ __forceinline__ void load_step(step_regs& r, const uint32_t* step, int lane) {
+  r.I = __ldcs(reinterpret_cast<const uint4*>(step) + lane);
+  r.V = __ldcs(reinterpret_cast<const float4*>(step + kStep) + lane);
+}
+
+template <int WARPS, int DEPTH, bool PROFILE = false>
 __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const params p) {
   extern __shared__ __align__(16) unsigned char bt_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x;
   const int rbi = cta / p.q, qi = cta - rbi * p.q;
-  const int row0 = rbi * p.rb;
-  const int rows_here = min(p.rb, p.rows - row0);
-  if (rows_here <= 0) return;  // whole row block past the end: nothing to write
+  const int row0 = p.blk_begin[rbi];
+  const int rows_here = p.blk_begin[rbi + 1] - row0;
+  if (rows_here <= 0) return;  // empty row block: nothing to write
+  auto wall_ns = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; };
+  long long* stamps = (PROFILE && p.prof) ? p.prof + size_t(gridDim.x) * WARPS * 8 + size_t(cta) * 4 : nullptr;
+  if (PROFILE && stamps && tid == 0) stamps[0] = wall_ns();
 
   // ---- carve shared memory (geom::smem_bytes order) ----
   uint64_t* xfull = reinterpret_cast<uint64_t*>(bt_smem);
   uint64_t* xempty = xfull + p.xb;
-  uint64_t* efull = xempty + p.xb;
-  const int nbar = (2 * p.xb + WARPS * p.es + 1) & ~1;
-  uint32_t* ering = reinterpret_cast<uint32_t*>(xfull + nbar);
-  float* xs = reinterpret_cast<float*>(ering + WARPS * p.es * kStepWords);
+  const int nbar = (2 * p.xb + 1) & ~1;
+  float* xs = reinterpret_cast<float*>(xfull + nbar);
   float* ys = xs + (p.xb * p.cb + 4);
   const int ys_words = (p.rb + 1 + 3) & ~3;
   uint16_t* fs_s = reinterpret_cast<uint16_t*>(ys + ys_words);
@@ -293,7 +373,6 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
       loops::tma::barrier_init(&xfull[k], 1);
       loops::tma::barrier_init(&xempty[k], WARPS);
     }
-    for (int i = 0; i < WARPS * p.es; ++i) loops::tma::barrier_init(&efull[i], 1);
   }
   for (int i = tid; i < ys_words; i += (WARPS + 1) * 32) ys[i] = 0.f;
   if (tid < 4) xs[p.xb * p.cb + tid] = 0.f;
@@ -305,6 +384,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
     }
   }
   __syncthreads();
+  if (PROFILE && stamps && tid == 0) stamps[1] = wall_ns();
 
   if (warp == WARPS) {
     // ---- x producer: one thread walks the bands of this column part ----
@@ -312,9 +392,10 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
       const uint64_t keep = loops::tma::policy_evict_last();
       const int col0 = qi * p.cq;
       const int part_cols = min(p.cq, p.cols - col0);
+      int k = 0;
+      uint32_t par = 1;  // parity of the PREVIOUS use of slot k (first pass: nothing to wait for)
       for (int b = 0; b < p.nband; ++b) {
-        const int k = b % p.xb;
-        if (b >= p.xb) loops::tma::barrier_wait(&xempty[k], uint32_t((b / p.xb) - 1) & 1u);
+        if (b >= p.xb) loops::tma::barrier_wait_suspend(&xempty[k], par);
         const int c0 = b * p.cb;
         int n = min(p.cb, part_cols - c0);
         if (n < 0) n = 0;
@@ -328,6 +409,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
         } else {
           loops::tma::barrier_arrive(&xfull[k]);
         }
+        if (++k == p.xb) { k = 0; par ^= 1u; }
       }
     }
   } else {
@@ -335,19 +417,12 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
     const int ws = cta * WARPS + warp;
     const int sbase = p.stream_base[ws];
     const int nsteps = p.stream_base[ws + 1] - sbase;
-    uint32_t* ring = ering + warp * p.es * kStepWords;
-    uint64_t* ef = efull + warp * p.es;
     const uint32_t* src = p.steps + size_t(sbase) * kStepWords;
-    const uint64_t stream_policy = loops::tma::policy_evict_first();
-    if (lane == 0) {
-      const int pre = min(p.es, nsteps);
-      for (int s = 0; s < pre; ++s) {
-        loops::tma::barrier_arrive_expect_tx(&ef[s], kStepWords * 4u);
-        loops::tma::bulk_g2s_hint(ring + s * kStepWords, src + size_t(s) * kStepWords, kStepWords * 4u, &ef[s],
-                                  stream_policy);
-      }
-    }
-    const uint32_t* refill = src + size_t(p.es) * kStepWords;  // next step to request
+    step_regs buf[DEPTH];
+#pragma unroll
+    for (int k = 0; k < DEPTH; ++k)
+      if (k < nsteps) load_step(buf[k], src + size_t(k) * kStepWords, lane);
+    const uint32_t* refill = src + size_t(DEPTH) * kStepWords;  // next step to request
     const uint16_t* fsw = fs_s + warp * p.nband;
     const uint16_t* lew = le_s + warp * p.nband;
     constexpr int kNever = 0x7fffffff;
@@ -367,7 +442,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
     };
     auto acquire_upto = [&](int s) {               // acquire every band first needed at step <= s
       while (nfs <= s) {
-        loops::tma::barrier_wait(&xfull[acq_k], acq_par);
+        loops::tma::barrier_wait_suspend(&xfull[acq_k], acq_par);
         if (rel == acq) nle = int(lew[acq]);
         ++acq;
         if (++acq_k == p.xb) { acq_k = 0; acq_par ^= 1u; }
@@ -375,81 +450,113 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
         release_upto(s);
       }
     };
-    int st = 0;
-    uint32_t ph = 0;
-    long long t_stream = 0, t_band = 0, t_gather = 0, t_fast = 0, t_slow = 0, n_slow = 0, t0 = 0, t1 = 0;
+    long long t_band = 0, t_rmw = 0, n_slow = 0, t0 = 0;
     const long long t_begin = PROFILE ? clock64() : 0;
     const int scratch = p.rb;
-    for (int s = 0; s < nsteps; ++s) {
-      if (PROFILE) t0 = clock64();
-      loops::tma::barrier_wait(&ef[st], ph);
-      if (PROFILE) { t1 = clock64(); t_stream += t1 - t0; t0 = t1; }
-      uint32_t* stage = ring + st * kStepWords;
-      const uint4 I = reinterpret_cast<const uint4*>(stage)[lane];
-      const float4 V = reinterpret_cast<const float4*>(stage + kStep)[lane];
-      acquire_upto(s);
-      if (PROFILE) { t1 = clock64(); t_band += t1 - t0; t0 = t1; }
-      const float p0 = __fmul_rn(V.x, xs[I.x & 0xffffu]);
-      const float p1 = __fmul_rn(V.y, xs[I.y & 0xffffu]);
-      const float p2 = __fmul_rn(V.z, xs[I.z & 0xffffu]);
-      const float p3 = __fmul_rn(V.w, xs[I.w & 0xffffu]);
-      const int r0 = int((I.x >> 16) & 0x7fffu), r1 = int((I.y >> 16) & 0x7fffu);
-      const int r2 = int((I.z >> 16) & 0x7fffu), r3 = int((I.w >> 16) & 0x7fffu);
-      const uint32_t fl = (I.x | I.y | I.z | I.w) & kFlagBit;
-      const bool dirty = __any_sync(0xffffffffu, fl != 0u);  // also: every lane is done with the stage
-      if (lane == 0 && s + p.es < nsteps) {
-        loops::tma::barrier_arrive_expect_tx(&ef[st], kStepWords * 4u);
-        loops::tma::bulk_g2s_hint(stage, refill, kStepWords * 4u, &ef[st], stream_policy);
-      }
+    // Software pipeline: the x gathers of step s+1 are issued before the y
+    // updates of step s, so the two shared-memory dependency chains overlap.
+    // `cur` = ids and products of the step whose y updates come next.
+    uint4 cI = make_uint4(0, 0, 0, 0);
+    float cp0 = 0.f, cp1 = 0.f, cp2 = 0.f, cp3 = 0.f;
+    if (nsteps > 0) {
+      cI = buf[0].I;
+      const float4 V = buf[0].V;
+      if (DEPTH < nsteps) load_step(buf[0], refill, lane);
       refill += kStepWords;
-      if (PROFILE) { t1 = clock64(); t_gather += t1 - t0; t0 = t1; }
-      if (!dirty) {
-        // Clean step: a row's entries are one contiguous slot range over at most
-        // two adjacent lanes. Sum runs inside the lane, hand a run that started in
-        // the previous lane to that lane, then update distinct y rows independently.
-        const bool c1 = r1 == r0, c2 = r2 == r1, c3 = r3 == r2;
-        const float v0 = p0;
-        const float v1 = c1 ? v0 + p1 : p1;
-        const float v2 = c2 ? v1 + p2 : p2;
-        float v3 = c3 ? v2 + p3 : p3;
-        bool o0 = !c1, o1 = !c2, o2 = !c3, o3 = true;   // slot closes its run
-        const int prev_last = __shfl_up_sync(0xffffffffu, r3, 1);
-        const bool hc = lane > 0 && prev_last == r0;     // my first run continues the previous lane's last
-        const float hv = o0 ? v0 : (o1 ? v1 : (o2 ? v2 : v3));
-        float recv = __shfl_down_sync(0xffffffffu, hc ? hv : 0.f, 1);
-        if (lane == 31) recv = 0.f;
-        if (hc) {                                        // that run is written by the previous lane
-          if (o0) o0 = false; else if (o1) o1 = false; else if (o2) o2 = false; else o3 = false;
+      acquire_upto(0);
+      cp0 = __fmul_rn(V.x, xs[cI.x & 0xffffu]);
+      cp1 = __fmul_rn(V.y, xs[cI.y & 0xffffu]);
+      cp2 = __fmul_rn(V.z, xs[cI.z & 0xffffu]);
+      cp3 = __fmul_rn(V.w, xs[cI.w & 0xffffu]);
+      __syncwarp();
+      release_upto(1);
+    }
+    for (int s0 = 0; s0 < nsteps; s0 += DEPTH) {
+#pragma unroll
+      for (int k = 0; k < DEPTH; ++k) {
+        const int s = s0 + k;
+        if (s >= nsteps) break;
+        const int kn = (k + 1) % DEPTH;          // buffer of step s + 1
+        const bool have_next = s + 1 < nsteps;
+        uint4 nI = make_uint4(0, 0, 0, 0);
+        float4 nV = make_float4(0.f, 0.f, 0.f, 0.f);
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+        if (have_next) {
+          nI = buf[kn].I;
+          nV = buf[kn].V;
+          if (s + 1 + DEPTH < nsteps) load_step(buf[kn], refill, lane);   // DEPTH steps ahead
+          refill += kStepWords;
+          if (PROFILE) t0 = clock64();
+          acquire_upto(s + 1);
+          if (PROFILE) t_band += clock64() - t0;
+          x0 = xs[nI.x & 0xffffu];
+          x1 = xs[nI.y & 0xffffu];
+          x2 = xs[nI.z & 0xffffu];
+          x3 = xs[nI.w & 0xffffu];
         }
-        v3 += recv;
-        const float y0 = ys[o0 ? r0 : scratch], y1 = ys[o1 ? r1 : scratch];
-        const float y2 = ys[o2 ? r2 : scratch], y3 = ys[o3 ? r3 : scratch];
-        if (o0) ys[r0] = y0 + v0;
-        if (o1) ys[r1] = y1 + v1;
-        if (o2) ys[r2] = y2 + v2;
-        if (o3) ys[r3] = y3 + v3;
-        if (PROFILE) { t1 = clock64(); t_fast += t1 - t0; t0 = t1; }
-      } else {
-        rmw_general(ys, r0, p0, scratch);
-        rmw_general(ys, r1, p1, scratch);
-        rmw_general(ys, r2, p2, scratch);
-        rmw_general(ys, r3, p3, scratch);
-        if (PROFILE) { t1 = clock64(); t_slow += t1 - t0; t0 = t1; ++n_slow; }
+        // ---- y updates of step s ----
+        if (PROFILE) t0 = clock64();
+        const int r0 = int((cI.x >> 16) & 0x7fffu), r1 = int((cI.y >> 16) & 0x7fffu);
+        const int r2 = int((cI.z >> 16) & 0x7fffu), r3 = int((cI.w >> 16) & 0x7fffu);
+        const uint32_t fl = (cI.x | cI.y | cI.z | cI.w) & kFlagBit;
+        const bool dirty = __any_sync(0xffffffffu, fl != 0u);
+        if (!dirty) {
+          // Clean step: a row's entries are one contiguous slot range over at most
+          // two adjacent lanes. Sum runs inside the lane, hand a run that started in
+          // the previous lane to that lane, then update distinct y rows independently.
+          const bool c1 = r1 == r0, c2 = r2 == r1, c3 = r3 == r2;
+          const float v0 = cp0;
+          const float v1 = c1 ? v0 + cp1 : cp1;
+          const float v2 = c2 ? v1 + cp2 : cp2;
+          float v3 = c3 ? v2 + cp3 : cp3;
+          const int prev_last = __shfl_up_sync(0xffffffffu, r3, 1);
+          const bool hc = (lane > 0) & (prev_last == r0);  // my first run continues the previous lane's last
+          // slot that closes the lane's FIRST run (exactly one of h0..h3 is set)
+          const bool h0 = !c1, h1 = c1 & !c2, h2 = c1 & c2 & !c3, h3 = c1 & c2 & c3;
+          const float hv = h0 ? v0 : (h1 ? v1 : (h2 ? v2 : v3));
+          float recv = __shfl_down_sync(0xffffffffu, hc ? hv : 0.f, 1);
+          recv = lane == 31 ? 0.f : recv;
+          v3 += recv;
+          // a slot writes y when it closes a run that this lane owns; everything
+          // else is pointed at the scratch row (branch-free, no predicates)
+          const int a0 = (!c1 & !(hc & h0)) ? r0 : scratch;
+          const int a1 = (!c2 & !(hc & h1)) ? r1 : scratch;
+          const int a2 = (!c3 & !(hc & h2)) ? r2 : scratch;
+          const int a3 = !(hc & h3) ? r3 : scratch;
+          const float y0 = ys[a0], y1 = ys[a1], y2 = ys[a2], y3 = ys[a3];
+          ys[a0] = y0 + v0;
+          ys[a1] = y1 + v1;
+          ys[a2] = y2 + v2;
+          ys[a3] = y3 + v3;
+        } else {
+          rmw_general(ys, r0, cp0, scratch);
+          rmw_general(ys, r1, cp1, scratch);
+          rmw_general(ys, r2, cp2, scratch);
+          rmw_general(ys, r3, cp3, scratch);
+          if (PROFILE) ++n_slow;
+        }
+        if (PROFILE) t_rmw += clock64() - t0;
+        // ---- products of step s + 1; its bands may now be released ----
+        cI = nI;
+        cp0 = __fmul_rn(nV.x, x0);
+        cp1 = __fmul_rn(nV.y, x1);
+        cp2 = __fmul_rn(nV.z, x2);
+        cp3 = __fmul_rn(nV.w, x3);
+        __syncwarp();   // y rows of step s settled, x values of step s + 1 consumed
+        if (have_next) release_upto(s + 2);
       }
-      __syncwarp();   // y rows of this step are settled before the next step's loads
-      release_upto(s + 1);
-      if (++st == p.es) { st = 0; ph ^= 1u; }
     }
     // bands after the warp's last step: keep the ring protocol going
     acquire_upto(kNever - 1);
     release_upto(kNever - 1);
     if (PROFILE && lane == 0 && p.prof) {
       long long* o = p.prof + size_t(ws) * 8;
-      o[0] = t_stream; o[1] = t_band; o[2] = t_gather; o[3] = t_fast; o[4] = t_slow; o[5] = n_slow;
+      o[0] = 0; o[1] = t_band; o[2] = 0; o[3] = t_rmw; o[4] = 0; o[5] = n_slow;
       o[6] = clock64() - t_begin; o[7] = nsteps;
     }
   }
   __syncthreads();
+  if (PROFILE && stamps && tid == 0) stamps[2] = wall_ns();
 
   // ---- write-out ----
   constexpr int NT = (WARPS + 1) * 32;
@@ -498,6 +605,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
     }
     if (tid == 0) p.counters[rbi] = 0u;  // ready for the next launch
   }
+  if (PROFILE && stamps) { __syncthreads(); if (tid == 0) stamps[3] = wall_ns(); }
 }
 
 // ---------------------------------------------------------------------------
@@ -507,6 +615,7 @@ struct plan_data {
   geom g;
   uint32_t* steps = nullptr;
   int32_t* stream_base = nullptr;
+  int32_t* blk_begin = nullptr;
   uint16_t* fs = nullptr;
   uint16_t* le = nullptr;
   float* partial = nullptr;
@@ -521,20 +630,30 @@ struct plan_data {
 
 inline void destroy(plan_data* d) {
   if (!d) return;
-  cudaFree(d->steps); cudaFree(d->stream_base); cudaFree(d->fs); cudaFree(d->le);
+  cudaFree(d->steps); cudaFree(d->stream_base); cudaFree(d->blk_begin); cudaFree(d->fs); cudaFree(d->le);
   cudaFree(d->partial); cudaFree(d->counters); cudaFree(d->prof);
   delete d;
 }
 
 using kernel_fn = void (*)(const params);
-inline kernel_fn kernel_for(int warps, bool profile = false) {
+template <int WARPS>
+inline kernel_fn kernel_for_depth(int depth, bool profile) {
+  switch (depth) {
+    case 2: return profile ? spmv_bt_kernel<WARPS, 2, true> : spmv_bt_kernel<WARPS, 2>;
+    case 3: return profile ? spmv_bt_kernel<WARPS, 3, true> : spmv_bt_kernel<WARPS, 3>;
+    case 4: return profile ? spmv_bt_kernel<WARPS, 4, true> : spmv_bt_kernel<WARPS, 4>;
+    default: return nullptr;
+  }
+}
+// warps: consumer warps per CTA; depth (geom::es): steps prefetched in registers.
+inline kernel_fn kernel_for(int warps, int depth, bool profile = false) {
   switch (warps) {
-    case 4: return profile ? spmv_bt_kernel<4, true> : spmv_bt_kernel<4>;
-    case 8: return profile ? spmv_bt_kernel<8, true> : spmv_bt_kernel<8>;
-    case 12: return profile ? spmv_bt_kernel<12, true> : spmv_bt_kernel<12>;
-    case 16: return profile ? spmv_bt_kernel<16, true> : spmv_bt_kernel<16>;
-    case 20: return profile ? spmv_bt_kernel<20, true> : spmv_bt_kernel<20>;
-    case 24: return profile ? spmv_bt_kernel<24, true> : spmv_bt_kernel<24>;
+    case 4: return kernel_for_depth<4>(depth, profile);
+    case 8: return kernel_for_depth<8>(depth, profile);
+    case 12: return kernel_for_depth<12>(depth, profile);
+    case 16: return kernel_for_depth<16>(depth, profile);
+    case 20: return kernel_for_depth<20>(depth, profile);
+    case 24: return kernel_for_depth<24>(depth, profile);
     default: return nullptr;
   }
 }
@@ -545,7 +664,7 @@ inline kernel_fn kernel_for(int warps, bool profile = false) {
 inline geom choose_geom(int rows, int cols, int sms, int max_smem) {
   geom g;
   g.q = (sms % 4 == 0) ? 4 : (sms % 2 == 0 ? 2 : 1);
-  g.warps = 16;
+  g.warps = 20;
   g.xb = 4;
   g.es = 2;
   int over[6] = {0, 0, 0, 0, 0, 0};
@@ -559,10 +678,9 @@ inline geom choose_geom(int rows, int cols, int sms, int max_smem) {
     g.nb = over[0];
   } else {
     // whole waves of CTAs (grid = nb*q = waves * sms); as few row blocks as the
-    // y rows in shared memory allow, keeping >= 48 KB for the x ring
+    // y rows in shared memory allow, keeping >= 64 KB for the x ring
     const int per_wave = std::max(1, sms / g.q);
-    const int ring = g.warps * g.es * kStepWords * 4;
-    int rb_cap = (max_smem - ring - 48 * 1024 - 4096) / 4;
+    int rb_cap = (max_smem - 64 * 1024 - 8192) / 4;
     rb_cap = std::max(256, std::min(rb_cap, kMaxRowsPerBlock));
     int waves = 1;
     while (ceil_div(rows, (long long)per_wave * waves) > rb_cap) ++waves;

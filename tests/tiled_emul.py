@@ -24,7 +24,7 @@ def build_image(lib, rows, cols, off, idx, val, geometry):
         return rc, None
     info = _lib.TiledInfo()
     assert lib.loopsb_tiled_image_info(h, C.byref(info)) == 0
-    ps = [C.c_void_p() for _ in range(4)]
+    ps = [C.c_void_p() for _ in range(6)]
     assert lib.loopsb_tiled_image_arrays(h, *[C.byref(p) for p in ps]) == 0
     g = info.as_dict()
     ns = g["nb"] * g["q"] * g["warps"]
@@ -40,6 +40,8 @@ def build_image(lib, rows, cols, off, idx, val, geometry):
         "stream_base": arr(ps[1], ns + 1, C.c_int32, np.int64),
         "fs": arr(ps[2], ns * g["nband"], C.c_uint16, np.int64).reshape(ns, g["nband"]),
         "le": arr(ps[3], ns * g["nband"], C.c_uint16, np.int64).reshape(ns, g["nband"]),
+        "blk_begin": arr(ps[4], g["nb"] + 1, C.c_int32, np.int64),
+        "warp_begin": arr(ps[5], g["nb"] * g["q"] * (g["warps"] + 1), C.c_int32, np.int64).reshape(-1, g["warps"] + 1),
     }
     lib.loopsb_tiled_image_free(h)
     return 0, img
@@ -51,12 +53,16 @@ def emulate(img, x, rows, cols):
     nb, q, W, cb, xb = g["nb"], g["q"], g["warps"], g["cb"], g["xb"]
     rb, rw, cq, nband = g["rb"], g["rw"], g["cq"], g["nband"]
     zero_slot = xb * cb
-    partial = np.zeros((q, nb * rb), np.float32)
+    blk = img["blk_begin"]
+    assert blk[0] == 0 and blk[-1] == rows and np.all(np.diff(blk) >= 0) and np.all(np.diff(blk) <= rb)
+    y_parts = np.zeros((q, rows), np.float32)
     out_r, out_c, out_v = [], [], []
     lane_of = np.repeat(np.arange(32), 4)
     for cta in range(nb * q):
         rbi, qi = divmod(cta, q)
         ys = np.zeros(rb + 1, np.float32)
+        wb = img["warp_begin"][cta]
+        assert wb[0] == 0 and wb[-1] == blk[rbi + 1] - blk[rbi] and np.all(np.diff(wb) >= 0)
         for w in range(W):
             s_id = cta * W + w
             base, end = img["stream_base"][s_id], img["stream_base"][s_id + 1]
@@ -85,9 +91,9 @@ def emulate(img, x, rows, cols):
                 assert np.all(band[real] >= rel), ("entry of a released band", cta, w, s)
                 assert np.all(band[real] >= 0)
                 col = qi * cq + band * cb + (lc_enc - k * cb)
-                row = rbi * rb + lr
+                row = blk[rbi] + lr
                 assert np.all(col[real] < cols) and np.all(row[real] < rows)
-                assert np.all((lr[real] // rw) == w), "row outside the warp's sub-block"
+                assert np.all((lr[real] >= wb[w]) & (lr[real] < wb[w + 1])), "row outside the warp's sub-block"
                 xv = np.where(real, x[np.where(real, col, 0)], np.float32(0)).astype(np.float32)
                 prod = (vals * xv).astype(np.float32)
                 # rows that the fast path cannot combine: not one contiguous slot
@@ -141,11 +147,11 @@ def emulate(img, x, rows, cols):
                     assert le[rel] <= nsteps
                     rel += 1
             assert rel == acq == nband or nband == 0 or rel <= acq
-        partial[qi, rbi * rb: rbi * rb + rb] = ys[:rb]
-    y = partial[0].copy()
+        y_parts[qi, blk[rbi]: blk[rbi + 1]] = ys[: blk[rbi + 1] - blk[rbi]]
+    y = y_parts[0].copy()
     for qq in range(1, q):
-        y = (y + partial[qq]).astype(np.float32)
+        y = (y + y_parts[qq]).astype(np.float32)
     tr = np.stack([np.concatenate(out_r) if out_r else np.zeros(0, np.int64),
                    np.concatenate(out_c) if out_c else np.zeros(0, np.int64),
                    np.concatenate(out_v).astype(np.int64) if out_v else np.zeros(0, np.int64)], axis=1)
-    return y[:rows], tr
+    return y, tr

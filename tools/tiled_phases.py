@@ -20,8 +20,14 @@ for geo in sys.argv[1:] or ["0,0,0,0,0,0"]:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); spmv.merge_path_flat(A, x, y, sync=False, tiled=True); e1.record(); torch.cuda.synchronize()
     ns = info["nb"] * info["q"] * info["warps"]
-    out = np.zeros((ns, 8), np.int64)
-    _lib.check(_lib.load().loopsb_plan_debug_phases_host(plan.handle, out.ctypes.data, ns), "phases")
+    grid = info["nb"] * info["q"]
+    raw = np.zeros(ns * 8 + ((grid * 4 + 7) // 8) * 8, np.int64)
+    _lib.check(_lib.load().loopsb_plan_debug_phases_host(plan.handle, raw.ctypes.data, raw.size // 8), "phases")
+    out = raw[: ns * 8].reshape(ns, 8)
+    st = raw[ns * 8: ns * 8 + grid * 4].reshape(grid, 4).astype(float)
+    t0 = st[:, 0].min()
+    print(f"   wall clock (us from first CTA entry): entry max {(st[:,0].max()-t0)/1e3:.1f}; init done mean {(st[:,1]-t0).mean()/1e3:.1f} max {(st[:,1]-t0).max()/1e3:.1f}; "
+          f"loop done mean {(st[:,2]-t0).mean()/1e3:.1f} min {(st[:,2]-t0).min()/1e3:.1f} max {(st[:,2]-t0).max()/1e3:.1f}; CTA end mean {(st[:,3]-t0).mean()/1e3:.1f} max {(st[:,3]-t0).max()/1e3:.1f}")
     steps = out[:, 7].astype(float); m = steps > 0
     print(f"{geo}: launch {e0.elapsed_time(e1)*1e3:.1f} us (profiled build); warps {ns}, steps/warp {steps[m].mean():.1f}, "
           f"warp total cycles mean {out[m,6].mean():.0f} max {out[:,6].max()}")
