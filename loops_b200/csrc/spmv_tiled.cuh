@@ -453,62 +453,39 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
     long long t_band = 0, t_rmw = 0, n_slow = 0, t0 = 0;
     const long long t_begin = PROFILE ? clock64() : 0;
     const int scratch = p.rb;
-    // Software pipeline: the x gathers of step s+1 are issued before the y
-    // updates of step s, so the two shared-memory dependency chains overlap.
-    // `cur` = ids and products of the step whose y updates come next.
-    uint4 cI = make_uint4(0, 0, 0, 0);
-    float cp0 = 0.f, cp1 = 0.f, cp2 = 0.f, cp3 = 0.f;
-    if (nsteps > 0) {
-      cI = buf[0].I;
-      const float4 V = buf[0].V;
-      if (DEPTH < nsteps) load_step(buf[0], refill, lane);
-      refill += kStepWords;
-      acquire_upto(0);
-      cp0 = __fmul_rn(V.x, xs[cI.x & 0xffffu]);
-      cp1 = __fmul_rn(V.y, xs[cI.y & 0xffffu]);
-      cp2 = __fmul_rn(V.z, xs[cI.z & 0xffffu]);
-      cp3 = __fmul_rn(V.w, xs[cI.w & 0xffffu]);
-      __syncwarp();
-      release_upto(1);
-    }
+    // (Issuing the x gathers of step s+1 ahead of the y updates of step s was
+    // tried and measured slower: a warp that then blocks on the x ring sits on
+    // y updates it could have retired. Steps are processed one at a time.)
     for (int s0 = 0; s0 < nsteps; s0 += DEPTH) {
 #pragma unroll
       for (int k = 0; k < DEPTH; ++k) {
         const int s = s0 + k;
         if (s >= nsteps) break;
-        const int kn = (k + 1) % DEPTH;          // buffer of step s + 1
-        const bool have_next = s + 1 < nsteps;
-        uint4 nI = make_uint4(0, 0, 0, 0);
-        float4 nV = make_float4(0.f, 0.f, 0.f, 0.f);
-        float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
-        if (have_next) {
-          nI = buf[kn].I;
-          nV = buf[kn].V;
-          if (s + 1 + DEPTH < nsteps) load_step(buf[kn], refill, lane);   // DEPTH steps ahead
-          refill += kStepWords;
-          if (PROFILE) t0 = clock64();
-          acquire_upto(s + 1);
-          if (PROFILE) t_band += clock64() - t0;
-          x0 = xs[nI.x & 0xffffu];
-          x1 = xs[nI.y & 0xffffu];
-          x2 = xs[nI.z & 0xffffu];
-          x3 = xs[nI.w & 0xffffu];
-        }
-        // ---- y updates of step s ----
+        const uint4 I = buf[k].I;
+        const float4 V = buf[k].V;
+        if (s + DEPTH < nsteps) load_step(buf[k], refill, lane);   // DEPTH steps ahead
+        refill += kStepWords;
         if (PROFILE) t0 = clock64();
-        const int r0 = int((cI.x >> 16) & 0x7fffu), r1 = int((cI.y >> 16) & 0x7fffu);
-        const int r2 = int((cI.z >> 16) & 0x7fffu), r3 = int((cI.w >> 16) & 0x7fffu);
-        const uint32_t fl = (cI.x | cI.y | cI.z | cI.w) & kFlagBit;
+        acquire_upto(s);
+        if (PROFILE) t_band += clock64() - t0;
+        const float p0 = __fmul_rn(V.x, xs[I.x & 0xffffu]);
+        const float p1 = __fmul_rn(V.y, xs[I.y & 0xffffu]);
+        const float p2 = __fmul_rn(V.z, xs[I.z & 0xffffu]);
+        const float p3 = __fmul_rn(V.w, xs[I.w & 0xffffu]);
+        const int r0 = int((I.x >> 16) & 0x7fffu), r1 = int((I.y >> 16) & 0x7fffu);
+        const int r2 = int((I.z >> 16) & 0x7fffu), r3 = int((I.w >> 16) & 0x7fffu);
+        const uint32_t fl = (I.x | I.y | I.z | I.w) & kFlagBit;
         const bool dirty = __any_sync(0xffffffffu, fl != 0u);
+        if (PROFILE) t0 = clock64();
         if (!dirty) {
           // Clean step: a row's entries are one contiguous slot range over at most
           // two adjacent lanes. Sum runs inside the lane, hand a run that started in
           // the previous lane to that lane, then update distinct y rows independently.
           const bool c1 = r1 == r0, c2 = r2 == r1, c3 = r3 == r2;
-          const float v0 = cp0;
-          const float v1 = c1 ? v0 + cp1 : cp1;
-          const float v2 = c2 ? v1 + cp2 : cp2;
-          float v3 = c3 ? v2 + cp3 : cp3;
+          const float v0 = p0;
+          const float v1 = c1 ? v0 + p1 : p1;
+          const float v2 = c2 ? v1 + p2 : p2;
+          float v3 = c3 ? v2 + p3 : p3;
           const int prev_last = __shfl_up_sync(0xffffffffu, r3, 1);
           const bool hc = (lane > 0) & (prev_last == r0);  // my first run continues the previous lane's last
           // slot that closes the lane's FIRST run (exactly one of h0..h3 is set)
@@ -529,21 +506,15 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
           ys[a2] = y2 + v2;
           ys[a3] = y3 + v3;
         } else {
-          rmw_general(ys, r0, cp0, scratch);
-          rmw_general(ys, r1, cp1, scratch);
-          rmw_general(ys, r2, cp2, scratch);
-          rmw_general(ys, r3, cp3, scratch);
+          rmw_general(ys, r0, p0, scratch);
+          rmw_general(ys, r1, p1, scratch);
+          rmw_general(ys, r2, p2, scratch);
+          rmw_general(ys, r3, p3, scratch);
           if (PROFILE) ++n_slow;
         }
         if (PROFILE) t_rmw += clock64() - t0;
-        // ---- products of step s + 1; its bands may now be released ----
-        cI = nI;
-        cp0 = __fmul_rn(nV.x, x0);
-        cp1 = __fmul_rn(nV.y, x1);
-        cp2 = __fmul_rn(nV.z, x2);
-        cp3 = __fmul_rn(nV.w, x3);
-        __syncwarp();   // y rows of step s settled, x values of step s + 1 consumed
-        if (have_next) release_upto(s + 2);
+        __syncwarp();   // y rows of this step are settled before the next step's loads
+        release_upto(s + 1);
       }
     }
     // bands after the warp's last step: keep the ring protocol going

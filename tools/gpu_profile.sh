@@ -6,8 +6,11 @@ timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/b
 timeout 900 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; cat gpurun_out/bench_n1.json | cut -c1-400
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"spmv_|merge_|bcsr" -c 60 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:spmv_merge_kernel -s 4 -c 2 -f -o gpurun_out/prof_merge \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:spmv_bt_kernel -s 4 -c 2 -f -o gpurun_out/prof_tiled \
+    python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_tiled.log 2>&1; echo "ncu tiled rc=$?"
+LOOPSB_TILED=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:spmv_merge_kernel -s 4 -c 2 -f -o gpurun_out/prof_merge \
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu merge rc=$?"
+LOOPSB_TILED=0 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/bench_n1_plain.json 2> gpurun_out/bench_n1_plain.err; echo "bench plain rc=$?"; cut -c1-300 gpurun_out/bench_n1_plain.json
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:bcsr4x4 -s 2 -c 2 -f -o gpurun_out/prof_bcsr \
     python tools/run_bcsr.py 5 > gpurun_out/ncu_bcsr.log 2>&1; echo "ncu bcsr rc=$?"
 ls -la gpurun_out/*.ncu-rep
