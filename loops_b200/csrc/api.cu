@@ -200,7 +200,7 @@ void free_probes(loopsb_plan* p) {
 namespace {
 int launch_tiled(bt::plan_data* d, const float* x, float* y, cudaStream_t s) {
   bt::params p;
-  p.steps = d->steps; p.stream_base = d->stream_base; p.blk_begin = d->blk_begin; p.fs = d->fs; p.le = d->le;
+  p.steps = d->steps; p.stream_base = d->stream_base; p.blk_begin = d->blk_begin; 
   p.x = x; p.y = y; p.partial = d->partial; p.counters = d->counters;
   p.rows = d->g.rows; p.cols = d->g.cols; p.rb = d->g.rb; p.cq = d->g.cq; p.cb = d->g.cb;
   p.xb = d->g.xb; p.es = d->g.es; p.nband = d->g.nband; p.q = d->g.q; p.nb = d->g.nb;
@@ -240,6 +240,7 @@ int loopsb_tiled_image_build_host(int32_t num_rows, int32_t num_cols, const int3
   bt::geom g;
   g.nb = geometry[0]; g.q = geometry[1]; g.warps = geometry[2];
   g.cb = geometry[3]; g.xb = geometry[4]; g.es = geometry[5];
+  if (const char* e = getenv("LOOPSB_TILED_PACK")) g.pack = atoi(e) != 0;
   int rc = LOOPSB_OK;
   try {
     rc = bt::build_host(img->im, g, num_rows, num_cols, host_offsets, host_indices, host_values);
@@ -358,12 +359,10 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const 
   d->smem = im.g.smem_bytes();
   auto fail = [&](int code) { bt::destroy(d); return code; };
   const size_t steps_b = im.steps.size() * 4, base_b = im.stream_base.size() * 4;
-  const size_t tab_b = im.fs.size() * 2;
   const size_t part_b = im.g.q > 1 ? size_t(im.g.q) * im.g.nb * ((im.g.rb + 3) & ~3) * 4 : 0;
   if (cudaMalloc(&d->steps, steps_b ? steps_b : 16) != cudaSuccess ||
       cudaMalloc(&d->stream_base, base_b) != cudaSuccess ||
       cudaMalloc(&d->blk_begin, im.blk_begin.size() * 4) != cudaSuccess ||
-      cudaMalloc(&d->fs, tab_b ? tab_b : 16) != cudaSuccess || cudaMalloc(&d->le, tab_b ? tab_b : 16) != cudaSuccess ||
       (part_b && cudaMalloc(&d->partial, part_b) != cudaSuccess) ||
       (part_b && cudaMalloc(&d->counters, size_t(im.g.nb) * 4) != cudaSuccess)) {
     (void)cudaGetLastError();
@@ -373,8 +372,6 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const 
   if (cudaMemcpy(d->steps, im.steps.data(), steps_b, cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(d->stream_base, im.stream_base.data(), base_b, cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(d->blk_begin, im.blk_begin.data(), im.blk_begin.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMemcpy(d->fs, im.fs.data(), tab_b, cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMemcpy(d->le, im.le.data(), tab_b, cudaMemcpyHostToDevice) != cudaSuccess ||
       (part_b && cudaMemset(d->counters, 0, size_t(im.g.nb) * 4) != cudaSuccess)) {
     set_error("upload of the band-tiled copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     return fail(LOOPSB_ERR_CUDA);
@@ -393,7 +390,7 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const 
   d->key_values = values;
   d->total_steps = im.total_steps; d->real_entries = im.real_entries; d->pad_entries = im.pad_entries;
   d->flagged_entries = im.flagged_entries; d->flagged_steps = im.flagged_steps;
-  d->bytes = (long long)(steps_b + base_b + 2 * tab_b + part_b + (part_b ? size_t(im.g.nb) * 4 : 0));
+  d->bytes = (long long)(steps_b + base_b + part_b + (part_b ? size_t(im.g.nb) * 4 : 0));
   if (plan->tiled) bt::destroy(plan->tiled);
   plan->tiled = d;
   return LOOPSB_OK;

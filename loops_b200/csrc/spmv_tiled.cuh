@@ -30,9 +30,10 @@
 // are one conflict-free 128-bit shared load and are consecutive in CSR order.
 //   id bits  0..15  position of x[col] in the x ring ((band % xb)*cb + col - band start)
 //      bits 16..30  row inside the CTA's row block
-//      bit  31      set on the entries of a row that the fast path cannot
-//                   combine inside the step (see "flags" in build_host); any
-//                   such entry sends the step down the general path
+//      bit  31      slots 1..3: zero. Slot 0: one bit of the step's 32-bit control
+//                   word, bit `lane` in lane `lane` (the warp reads it with one
+//                   ballot): dirty flag and the x-ring events of the step, see
+//                   meta_* below
 // Padding entries have value 0, point at a zero word behind the x ring and at a
 // scratch row behind the y rows, so they need no predicate.
 // A step only holds bands of one window of `xb` consecutive bands (the plan
@@ -55,12 +56,20 @@ constexpr int kPerLane = 4;
 constexpr int kStep = kLanes * kPerLane;  // entries per step
 constexpr int kStepWords = 2 * kStep;     // 256 words = 1 KB
 constexpr uint32_t kFlagBit = 0x80000000u;
+// Step control word (ballot of bit 31 of the slot-0 ids):
+//   bit 0       dirty: some row of the step cannot be combined by the fast path
+//   bits 1..12  lead : empty bands to acquire and release at once before the step
+//   bits 13..16 plen : bands that follow, first to last band STARTING in this step
+//   bits 17..24 pat  : bit i = band i of those has entries (held), 0 = empty (released at once)
+//   bits 25..28 nrel : held bands whose last entry is in this step (released after it, oldest first)
+constexpr int kMetaLeadShift = 1, kMetaLeadBits = 12, kMetaPlenShift = 13, kMetaPatShift = 17, kMetaRelShift = 25;
 constexpr int kMaxRowsPerBlock = 32767;   // 15 row bits, one value kept for the scratch row
 constexpr int kMaxRingFloats = 65532;     // 16 column bits, zero word behind the ring
 
 struct geom {
   // chosen
   int nb = 0, q = 0, warps = 0, cb = 0, xb = 0, es = 0;
+  int pack = 1;   // bank-aware placement of the entries inside a step (LOOPSB_TILED_PACK=0 turns it off)
   // derived
   int rb = 0, rw = 0, cq = 0, nband = 0;
   int rows = 0, cols = 0;
@@ -72,7 +81,7 @@ struct geom {
   int bar_count() const { return (2 * xb + 1) & ~1; }
   int ys_words() const { return (rb + 1 + 3) & ~3; }
   int xs_words() const { return xb * cb + 4; }
-  int table_bytes() const { return ((2 * warps * nband * 2 + 4) + 15) & ~15; }
+  int table_bytes() const { return 16; }   // the last-arriver flag of the q-way reduction
   int smem_bytes() const {
     return bar_count() * 8 + xs_words() * 4 + ys_words() * 4 + table_bytes();
   }
@@ -85,13 +94,14 @@ inline int ceil_div(long long a, long long b) { return int((a + b - 1) / b); }
 inline bool derive(geom& g, int rows, int cols, const char** why) {
   static const char* reasons[] = {"geometry fields must be positive", "cb must be a multiple of 4",
                                   "x ring exceeds 16 bits of position", "row block exceeds 15 bits of row",
-                                  "more than 31 consumer warps", "more than 8 column parts"};
+                                  "more than 31 consumer warps", "more than 4 column parts"};
   g.rows = rows; g.cols = cols;
   if (g.nb < 1 || g.q < 1 || g.warps < 1 || g.cb < 4 || g.xb < 2 || g.es < 2) { *why = reasons[0]; return false; }
   if (g.cb % 4) { *why = reasons[1]; return false; }
   if (g.xb * g.cb > kMaxRingFloats) { *why = reasons[2]; return false; }
   if (g.warps > 31) { *why = reasons[4]; return false; }
-  if (g.q > 8) { *why = reasons[5]; return false; }
+  if (g.q > 4) { *why = reasons[5]; return false; }
+  if (g.xb > 8) { *why = "x ring deeper than 8 bands"; return false; }
   // rb is an UPPER BOUND here (row blocks are cut by nonzero count, so a block
   // of light rows may hold up to ~15 % more rows than rows/nb); build_host
   // replaces it by the largest block actually cut.
@@ -214,7 +224,8 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
       pos = e;
       end[b] = e;
     }
-    const long long nsteps = (pos + kStep - 1) / kStep;
+    long long nsteps = (pos + kStep - 1) / kStep;
+    nsteps = (nsteps + g.es - 1) / g.es * g.es;   // whole prefetch groups (all-padding steps at the end)
     if (nsteps > 65535) { set_error("band-tiled plan: a warp stream needs %lld steps (> 65535)", nsteps); return LOOPSB_ERR_UNSUPPORTED; }
     // band tables: empty bands borrow the first step of the next non-empty one
     int next_fs = int(nsteps);
@@ -238,8 +249,8 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
   im.total_steps = total;
   // ---- pass 2: scatter (padding pre-filled) ----
   const uint32_t pad_id = (uint32_t(g.rb) << 16) | uint32_t(g.zero_slot());
-  im.steps.assign(size_t(total) * kStepWords, 0u);
-  for (long long s = 0; s < total; ++s) {
+  im.steps.assign(size_t(total + g.es) * kStepWords, 0u);   // + es steps the last prefetch may touch
+  for (long long s = 0; s < total + g.es; ++s) {
     uint32_t* w = &im.steps[size_t(s) * kStepWords];
     for (int i = 0; i < kStep; ++i) w[i] = pad_id;
   }
@@ -266,12 +277,121 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
   }
   im.real_entries = nnz;
   im.pad_entries = total * kStep - nnz;
-  // ---- pass 3: flags. A step is "clean" when every row it touches sits in ONE
-  // contiguous range of slots (slot = lane*4 + j, i.e. CSR order) that spans at
-  // most two adjacent lanes -- what the kernel's fast path can combine with a
-  // per-lane run sum and one neighbour shuffle. Entries of rows that break the
-  // rule (a row seen in two bands of the same step, or a run over 3+ lanes) get
-  // bit 31 and send the whole step down the general path. ----
+  // ---- pass 2b: pack every step for the shared-memory banks. Which of the 128
+  // cells (lane, slot j) of a step an entry sits in is free as long as a row's
+  // entries stay together, so entries are placed to spread the 32 lanes of each
+  // slot j over distinct banks of the x ring (bank = ring position mod 32) and of
+  // the y rows (bank = row mod 32, counted for the cell that closes the run):
+  // an instruction over 32 random banks costs ~3.4 shared-memory wavefronts, a
+  // packed one ~2. All entries of a row inside the step become ONE run (also when
+  // they come from two bands), longest runs are placed first, single entries go
+  // to the slot column where their two banks are least used. ----
+  if (g.pack) {
+    struct ent { uint32_t id, val; };
+    std::vector<int64_t> stamp(size_t(g.rb) + 1, -1);
+    std::vector<int32_t> unit_of(size_t(g.rb) + 1, 0);
+    std::vector<ent> in(kStep), out(kStep);
+    std::vector<int> unit_start, unit_len, order;
+    std::vector<ent> unit_ents;
+    const uint32_t pad_id2 = (uint32_t(g.rb) << 16) | uint32_t(g.zero_slot());
+    for (long long s = 0; s < total; ++s) {
+      uint32_t* w = &im.steps[size_t(s) * kStepWords];
+      // gather units (all entries of one row), preserving the stream order inside a unit
+      unit_start.clear(); unit_len.clear();
+      int nreal = 0;
+      for (int p = 0; p < kStep; ++p) {
+        in[p] = ent{w[p], w[kStep + p]};
+        const int lr = int((w[p] >> 16) & 0x7fff);
+        if (lr == g.rb) continue;
+        ++nreal;
+        if (stamp[lr] != s) { stamp[lr] = s; unit_of[lr] = int(unit_len.size()); unit_len.push_back(1); }
+        else ++unit_len[unit_of[lr]];
+      }
+      if (nreal == 0) continue;
+      const int nu = int(unit_len.size());
+      unit_start.assign(nu + 1, 0);
+      for (int u = 0; u < nu; ++u) unit_start[u + 1] = unit_start[u] + unit_len[u];
+      unit_ents.resize(nreal);
+      {
+        std::vector<int>& fill = order;   // reuse as per-unit cursor
+        fill.assign(nu, 0);
+        for (int p = 0; p < kStep; ++p) {
+          const int lr = int((in[p].id >> 16) & 0x7fff);
+          if (lr == g.rb) continue;
+          const int u = unit_of[lr];
+          unit_ents[unit_start[u] + fill[u]++] = in[p];
+        }
+      }
+      // units by decreasing length (counting sort on min(len, 9))
+      order.clear();
+      for (int L = 9; L >= 1; --L)
+        for (int u = 0; u < nu; ++u)
+          if (std::min(unit_len[u], 9) == L) order.push_back(u);
+      bool used[kLanes][kPerLane] = {};
+      int free_in_col[kPerLane] = {kLanes, kLanes, kLanes, kLanes};
+      int cx[kPerLane][32] = {}, cy[kPerLane][32] = {};
+      for (int p = 0; p < kStep; ++p) out[p] = ent{pad_id2, 0u};
+      auto xbank = [](const ent& e) { return int(e.id & 31u); };
+      auto ybank = [](const ent& e) { return int((e.id >> 16) & 31u); };
+      auto put = [&](int lane, int j, const ent& e, bool closes) {
+        used[lane][j] = true;
+        --free_in_col[j];
+        out[lane * kPerLane + j] = e;
+        ++cx[j][xbank(e)];
+        if (closes) ++cy[j][ybank(e)];
+      };
+      bool failed = false;
+      for (int u : order) {
+        const ent* e = &unit_ents[unit_start[u]];
+        const int L = unit_len[u];
+        if (L == 1) {
+          int best = -1, best_cost = 1 << 30;
+          for (int j = 0; j < kPerLane; ++j) {
+            if (free_in_col[j] == 0) continue;
+            const int cost = (cx[j][xbank(e[0])] + cy[j][ybank(e[0])]) * 64 - free_in_col[j];
+            if (cost < best_cost) { best_cost = cost; best = j; }
+          }
+          if (best < 0) { failed = true; break; }
+          int lane = 0;
+          while (used[lane][best]) ++lane;
+          put(lane, best, e[0], true);
+        } else if (L <= kPerLane) {
+          int bl = -1, bj = -1, best_cost = 1 << 30;
+          for (int lane = 0; lane < kLanes; ++lane)
+            for (int j = 0; j + L <= kPerLane; ++j) {
+              bool ok = true;
+              int cost = 0;
+              for (int i = 0; i < L; ++i) { ok = ok && !used[lane][j + i]; cost += cx[j + i][xbank(e[i])]; }
+              if (!ok) continue;
+              cost += cy[j + L - 1][ybank(e[L - 1])];
+              if (cost < best_cost) { best_cost = cost; bl = lane; bj = j; }
+            }
+          if (bl < 0) { failed = true; break; }
+          for (int i = 0; i < L; ++i) put(bl, bj + i, e[i], i == L - 1);
+        } else {
+          // long run: whole lanes from slot 0 on, contiguous (2 lanes stay clean, more are flagged later)
+          const int lanes_needed = (L + kPerLane - 1) / kPerLane;
+          int bl = -1;
+          for (int lane = 0; lane + lanes_needed <= kLanes && bl < 0; ++lane) {
+            bool ok = true;
+            for (int i = 0; i < L; ++i) ok = ok && !used[lane + i / kPerLane][i % kPerLane];
+            if (ok) bl = lane;
+          }
+          if (bl < 0) { failed = true; break; }
+          for (int i = 0; i < L; ++i) put(bl + i / kPerLane, i % kPerLane, e[i], i == kPerLane - 1);
+        }
+      }
+      if (failed) continue;   // keep the stream order for this step (always a legal layout)
+      for (int p = 0; p < kStep; ++p) { w[p] = out[p].id; w[kStep + p] = out[p].val; }
+    }
+  }
+  // ---- pass 3: control words. A step is "clean" when every row it touches sits
+  // in ONE contiguous range of cells (cell = lane*4 + j) that spans at most two
+  // adjacent lanes -- what the kernel's fast path can combine with a per-lane run
+  // sum and one neighbour shuffle; otherwise it is marked dirty and takes the
+  // general path. The x-ring events of the step (which bands the warp must wait
+  // for before it, which it is done with after it) come from the band tables. ----
+  std::vector<uint32_t> meta(size_t(total), 0u);
   {
     std::vector<int64_t> stamp(size_t(g.rb) + 1, -1);
     std::vector<int32_t> first(size_t(g.rb) + 1, 0), last(size_t(g.rb) + 1, 0), cnt(size_t(g.rb) + 1, 0);
@@ -289,10 +409,46 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
         if (lr == g.rb) continue;
         const bool bad = (last[lr] - first[lr] + 1 != cnt[lr]) ||
                          (last[lr] / kPerLane - first[lr] / kPerLane >= 2);
-        if (bad) { w[p] |= kFlagBit; ++im.flagged_entries; any = true; }
+        if (bad) { ++im.flagged_entries; any = true; }
       }
-      if (any) ++im.flagged_steps;
+      if (any) { ++im.flagged_steps; meta[size_t(s)] |= 1u; }
     }
+  }
+  for (int st = 0; st < ns; ++st) {
+    const long long base = im.stream_base[st];
+    const int nsteps = im.stream_base[st + 1] - im.stream_base[st];
+    const int32_t* cnt = &count[size_t(st) * nband];
+    const uint16_t* fs = &im.fs[size_t(st) * nband];
+    const uint16_t* le = &im.le[size_t(st) * nband];
+    int b = 0;
+    while (b < nband) {
+      const int step = fs[b];
+      if (step >= nsteps) break;   // trailing empty bands: acquired and released after the last step
+      // bands b .. e-1 all start (or, being empty, are borrowed) at `step`
+      int e = b;
+      while (e < nband && fs[e] == step) ++e;
+      int lead = 0;
+      while (b + lead < e && cnt[b + lead] == 0) ++lead;
+      const int plen = e - (b + lead);
+      if (lead >= (1 << kMetaLeadBits) || plen > 8) {
+        set_error("band-tiled plan: %d empty / %d starting bands in one step exceed the control word", lead, plen);
+        return LOOPSB_ERR_UNSUPPORTED;
+      }
+      uint32_t pat = 0;
+      for (int i = 0; i < plen; ++i)
+        if (cnt[b + lead + i] > 0) pat |= 1u << i;
+      meta[size_t(base + step)] |= (uint32_t(lead) << kMetaLeadShift) | (uint32_t(plen) << kMetaPlenShift) |
+                                   (pat << kMetaPatShift);
+      b = e;
+    }
+    for (int bb = 0; bb < nband; ++bb)
+      if (cnt[bb] > 0) meta[size_t(base + le[bb] - 1)] += 1u << kMetaRelShift;   // nrel <= xb <= 8 by the window rule
+  }
+  for (long long s = 0; s < total; ++s) {
+    uint32_t* w = &im.steps[size_t(s) * kStepWords];
+    const uint32_t m = meta[size_t(s)];
+    for (int lane = 0; lane < kLanes; ++lane)
+      if ((m >> lane) & 1u) w[lane * kPerLane] |= kFlagBit;
   }
   return LOOPSB_OK;
 }
@@ -304,8 +460,6 @@ struct params {
   const uint32_t* steps;
   const int32_t* stream_base;
   const int32_t* blk_begin;   // nb + 1 row-block boundaries
-  const uint16_t* fs;
-  const uint16_t* le;
   const float* x;
   float* y;
   float* partial;       // [q][nb*rb] when q > 1
@@ -318,7 +472,7 @@ struct params {
 // row. Lanes are grouped by row (match.any); the lowest lane of each group
 // updates, the rest retry, so equal rows are applied one after another in
 // lane order. Padding (scratch row) is skipped.
-__device__ __forceinline__ void rmw_general(float* ys, int r, float p, int scratch) {
+__device__ __noinline__ void rmw_general(float* ys, int r, float p, int scratch) {
   bool todo = r != scratch;
   unsigned pend = __ballot_sync(0xffffffffu, todo);
   while (pend) {
@@ -355,7 +509,10 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
   if (rows_here <= 0) return;  // empty row block: nothing to write
   auto wall_ns = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; };
   long long* stamps = (PROFILE && p.prof) ? p.prof + size_t(gridDim.x) * WARPS * 8 + size_t(cta) * 4 : nullptr;
-  if (PROFILE && stamps && tid == 0) stamps[0] = wall_ns();
+  // One-thread work (barrier set-up, stamps) is given to the producer warp, so no
+  // consumer warp ever enters its loop with a lane on a different control path.
+  const bool boss = tid == WARPS * 32;
+  if (PROFILE && stamps && boss) stamps[0] = wall_ns();
 
   // ---- carve shared memory (geom::smem_bytes order) ----
   uint64_t* xfull = reinterpret_cast<uint64_t*>(bt_smem);
@@ -364,11 +521,9 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
   float* xs = reinterpret_cast<float*>(xfull + nbar);
   float* ys = xs + (p.xb * p.cb + 4);
   const int ys_words = (p.rb + 1 + 3) & ~3;
-  uint16_t* fs_s = reinterpret_cast<uint16_t*>(ys + ys_words);
-  uint16_t* le_s = fs_s + WARPS * p.nband;
-  int* last_flag = reinterpret_cast<int*>(le_s + WARPS * p.nband);
+  int* last_flag = reinterpret_cast<int*>(ys + ys_words);
 
-  if (tid == 0) {
+  if (boss) {
     for (int k = 0; k < p.xb; ++k) {
       loops::tma::barrier_init(&xfull[k], 1);
       loops::tma::barrier_init(&xempty[k], WARPS);
@@ -376,15 +531,8 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
   }
   for (int i = tid; i < ys_words; i += (WARPS + 1) * 32) ys[i] = 0.f;
   if (tid < 4) xs[p.xb * p.cb + tid] = 0.f;
-  {
-    const size_t tb = size_t(cta) * WARPS * p.nband;
-    for (int i = tid; i < WARPS * p.nband; i += (WARPS + 1) * 32) {
-      fs_s[i] = p.fs[tb + i];
-      le_s[i] = p.le[tb + i];
-    }
-  }
   __syncthreads();
-  if (PROFILE && stamps && tid == 0) stamps[1] = wall_ns();
+  if (PROFILE && stamps && boss) stamps[1] = wall_ns();
 
   if (warp == WARPS) {
     // ---- x producer: one thread walks the bands of this column part ----
@@ -414,69 +562,79 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
     }
   } else {
     // ---- consumer warp: its own stream, its own rows ----
+    __syncwarp();
     const int ws = cta * WARPS + warp;
     const int sbase = p.stream_base[ws];
     const int nsteps = p.stream_base[ws + 1] - sbase;
     const uint32_t* src = p.steps + size_t(sbase) * kStepWords;
     step_regs buf[DEPTH];
 #pragma unroll
-    for (int k = 0; k < DEPTH; ++k)
-      if (k < nsteps) load_step(buf[k], src + size_t(k) * kStepWords, lane);
+    for (int k = 0; k < DEPTH; ++k) load_step(buf[k], src + size_t(k) * kStepWords, lane);
     const uint32_t* refill = src + size_t(DEPTH) * kStepWords;  // next step to request
-    const uint16_t* fsw = fs_s + warp * p.nband;
-    const uint16_t* lew = le_s + warp * p.nband;
-    constexpr int kNever = 0x7fffffff;
-    // x-ring bookkeeping without divisions: slot and parity of the next band to
-    // acquire / release, and the step numbers at which that happens.
-    int acq = 0, rel = 0, acq_k = 0, rel_k = 0;
-    uint32_t acq_par = 0;
-    int nfs = p.nband > 0 ? int(fsw[0]) : kNever;  // first step that needs band `acq`
-    int nle = kNever;                              // band `rel` is finished once s + 1 >= nle
-    auto release_upto = [&](int limit) {           // release bands whose le <= limit
-      while (nle <= limit) {
-        if (lane == 0) loops::tma::barrier_arrive(&xempty[rel_k]);
-        ++rel;
-        if (++rel_k == p.xb) rel_k = 0;
-        nle = rel < acq ? int(lew[rel]) : kNever;
-      }
+    // x-ring bookkeeping: ring slot / parity of the next band to acquire, and a
+    // FIFO (3 bits per entry) of the slots of the bands this warp still holds.
+    // What to do at each step comes from the step's control word.
+    int acq = 0, acq_k = 0, nheld = 0;
+    uint32_t acq_par = 0, held = 0;
+    auto advance = [&]() {
+      ++acq;
+      if (++acq_k == p.xb) { acq_k = 0; acq_par ^= 1u; }
     };
-    auto acquire_upto = [&](int s) {               // acquire every band first needed at step <= s
-      while (nfs <= s) {
+    auto band_events = [&](uint32_t m) {   // before the step's x gathers
+      const int lead = int((m >> kMetaLeadShift) & ((1u << kMetaLeadBits) - 1u));
+      const int plen = int((m >> kMetaPlenShift) & 0xfu);
+      const uint32_t pat = (m >> kMetaPatShift) & 0xffu;
+#pragma unroll 1
+      for (int i = 0; i < lead; ++i) {      // bands without entries for this warp
         loops::tma::barrier_wait_suspend(&xfull[acq_k], acq_par);
-        if (rel == acq) nle = int(lew[acq]);
-        ++acq;
-        if (++acq_k == p.xb) { acq_k = 0; acq_par ^= 1u; }
-        nfs = acq < p.nband ? int(fsw[acq]) : kNever;
-        release_upto(s);
+        if (lane == 0) loops::tma::barrier_arrive(&xempty[acq_k]);
+        advance();
+      }
+#pragma unroll 1
+      for (int i = 0; i < plen; ++i) {
+        loops::tma::barrier_wait_suspend(&xfull[acq_k], acq_par);
+        if ((pat >> i) & 1u) { held |= uint32_t(acq_k) << (3 * nheld); ++nheld; }
+        else if (lane == 0) loops::tma::barrier_arrive(&xempty[acq_k]);
+        advance();
       }
     };
-    long long t_band = 0, t_rmw = 0, n_slow = 0, t0 = 0;
+    auto release = [&](int n) {             // after the step: its x values are in registers
+#pragma unroll 1
+      for (int i = 0; i < n; ++i) {
+        if (lane == 0) loops::tma::barrier_arrive(&xempty[held & 7u]);
+        held >>= 3;
+        --nheld;
+      }
+    };
+    long long t_stream = 0, t_band = 0, t_gather = 0, t_rmw = 0, n_slow = 0, t0 = 0;
     const long long t_begin = PROFILE ? clock64() : 0;
     const int scratch = p.rb;
     // (Issuing the x gathers of step s+1 ahead of the y updates of step s was
     // tried and measured slower: a warp that then blocks on the x ring sits on
     // y updates it could have retired. Steps are processed one at a time.)
+    // nsteps is a multiple of DEPTH (the plan pads streams with all-padding steps)
+    // and DEPTH spare steps follow the last stream, so prefetches need no guard.
     for (int s0 = 0; s0 < nsteps; s0 += DEPTH) {
 #pragma unroll
       for (int k = 0; k < DEPTH; ++k) {
-        const int s = s0 + k;
-        if (s >= nsteps) break;
+        // (the step is used in place and its registers are re-loaded only when the
+        // step is done: copying them out first made ptxas rotate registers with
+        // moves that wait on the load just issued -- a synchronous "prefetch")
         const uint4 I = buf[k].I;
         const float4 V = buf[k].V;
-        if (s + DEPTH < nsteps) load_step(buf[k], refill, lane);   // DEPTH steps ahead
-        refill += kStepWords;
         if (PROFILE) t0 = clock64();
-        acquire_upto(s);
-        if (PROFILE) t_band += clock64() - t0;
+        const uint32_t m = __ballot_sync(0xffffffffu, (I.x & kFlagBit) != 0u);   // the step's control word
+        if (PROFILE) { const long long t1 = clock64(); t_stream += t1 - t0; t0 = t1; }
+        if (m >> kMetaLeadShift) band_events(m);
+        if (PROFILE) { const long long t1 = clock64(); t_band += t1 - t0; t0 = t1; }
         const float p0 = __fmul_rn(V.x, xs[I.x & 0xffffu]);
         const float p1 = __fmul_rn(V.y, xs[I.y & 0xffffu]);
         const float p2 = __fmul_rn(V.z, xs[I.z & 0xffffu]);
         const float p3 = __fmul_rn(V.w, xs[I.w & 0xffffu]);
         const int r0 = int((I.x >> 16) & 0x7fffu), r1 = int((I.y >> 16) & 0x7fffu);
         const int r2 = int((I.z >> 16) & 0x7fffu), r3 = int((I.w >> 16) & 0x7fffu);
-        const uint32_t fl = (I.x | I.y | I.z | I.w) & kFlagBit;
-        const bool dirty = __any_sync(0xffffffffu, fl != 0u);
-        if (PROFILE) t0 = clock64();
+        const bool dirty = (m & 1u) != 0u;
+        if (PROFILE) { const long long t1 = clock64(); t_gather += (p0 + p1 + p2 + p3 == 12345.f) ? 1 : t1 - t0; t0 = t1; }
         if (!dirty) {
           // Clean step: a row's entries are one contiguous slot range over at most
           // two adjacent lanes. Sum runs inside the lane, hand a run that started in
@@ -514,20 +672,27 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
         }
         if (PROFILE) t_rmw += clock64() - t0;
         __syncwarp();   // y rows of this step are settled before the next step's loads
-        release_upto(s + 1);
+        release(int(m >> kMetaRelShift) & 0xf);
+        load_step(buf[k], refill, lane);   // step s + DEPTH, into the registers just freed
+        refill += kStepWords;
       }
     }
-    // bands after the warp's last step: keep the ring protocol going
-    acquire_upto(kNever - 1);
-    release_upto(kNever - 1);
+    // bands after the warp's last step (none of them has entries for this warp):
+    // keep the ring protocol going
+    release(nheld);
+    while (acq < p.nband) {
+      loops::tma::barrier_wait_suspend(&xfull[acq_k], acq_par);
+      if (lane == 0) loops::tma::barrier_arrive(&xempty[acq_k]);
+      advance();
+    }
     if (PROFILE && lane == 0 && p.prof) {
       long long* o = p.prof + size_t(ws) * 8;
-      o[0] = 0; o[1] = t_band; o[2] = 0; o[3] = t_rmw; o[4] = 0; o[5] = n_slow;
+      o[0] = t_stream; o[1] = t_band; o[2] = t_gather; o[3] = t_rmw; o[4] = 0; o[5] = n_slow;
       o[6] = clock64() - t_begin; o[7] = nsteps;
     }
   }
   __syncthreads();
-  if (PROFILE && stamps && tid == 0) stamps[2] = wall_ns();
+  if (PROFILE && stamps && boss) stamps[2] = wall_ns();
 
   // ---- write-out ----
   constexpr int NT = (WARPS + 1) * 32;
@@ -555,28 +720,41 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
     __threadfence();
     const float4* part = reinterpret_cast<const float4*>(p.partial + size_t(rbi) * rb4);
     const size_t pitch4 = pitch >> 2;
-    for (int i = tid; i < n4; i += NT) {
-      float4 v[8];
+    // three row groups per thread and trip, all their partial loads issued before
+    // the first add: the reduction is latency-bound (L2 round trips), so the
+    // loads have to be in flight together
+    constexpr int U = 3;
+    for (int i0 = tid; i0 < n4; i0 += NT * U) {
+      float4 v[U][4];
 #pragma unroll
-      for (int qq = 0; qq < 8; ++qq)
-        if (qq < p.q && qq != qi) v[qq] = __ldcg(part + size_t(qq) * pitch4 + i);
-      float4 acc = (qi == 0) ? ys4[i] : v[0];
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * NT;
 #pragma unroll
-      for (int qq = 1; qq < 8; ++qq)
-        if (qq < p.q) {
-          const float4 t = (qq == qi) ? ys4[i] : v[qq];
-          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-        }
-      const int r = 4 * i;
-      float* out = p.y + row0 + r;
-      out[0] = acc.x;
-      if (r + 1 < rows_here) out[1] = acc.y;
-      if (r + 2 < rows_here) out[2] = acc.z;
-      if (r + 3 < rows_here) out[3] = acc.w;
+        for (int qq = 0; qq < 4; ++qq)
+          if (qq < p.q && qq != qi && i < n4) v[u][qq] = __ldcg(part + size_t(qq) * pitch4 + i);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * NT;
+        if (i >= n4) break;
+        float4 acc = (qi == 0) ? ys4[i] : v[u][0];
+#pragma unroll
+        for (int qq = 1; qq < 4; ++qq)
+          if (qq < p.q) {
+            const float4 t = (qq == qi) ? ys4[i] : v[u][qq];
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+          }
+        const int r = 4 * i;
+        float* out = p.y + row0 + r;
+        out[0] = acc.x;
+        if (r + 1 < rows_here) out[1] = acc.y;
+        if (r + 2 < rows_here) out[2] = acc.z;
+        if (r + 3 < rows_here) out[3] = acc.w;
+      }
     }
     if (tid == 0) p.counters[rbi] = 0u;  // ready for the next launch
   }
-  if (PROFILE && stamps) { __syncthreads(); if (tid == 0) stamps[3] = wall_ns(); }
+  if (PROFILE && stamps) { __syncthreads(); if (boss) stamps[3] = wall_ns(); }
 }
 
 // ---------------------------------------------------------------------------
@@ -587,8 +765,6 @@ struct plan_data {
   uint32_t* steps = nullptr;
   int32_t* stream_base = nullptr;
   int32_t* blk_begin = nullptr;
-  uint16_t* fs = nullptr;
-  uint16_t* le = nullptr;
   float* partial = nullptr;
   unsigned* counters = nullptr;
   const void* key_indices = nullptr;  // the CSR arrays this copy was made from
@@ -601,7 +777,7 @@ struct plan_data {
 
 inline void destroy(plan_data* d) {
   if (!d) return;
-  cudaFree(d->steps); cudaFree(d->stream_base); cudaFree(d->blk_begin); cudaFree(d->fs); cudaFree(d->le);
+  cudaFree(d->steps); cudaFree(d->stream_base); cudaFree(d->blk_begin); 
   cudaFree(d->partial); cudaFree(d->counters); cudaFree(d->prof);
   delete d;
 }
@@ -637,7 +813,7 @@ inline geom choose_geom(int rows, int cols, int sms, int max_smem) {
   g.q = (sms % 4 == 0) ? 4 : (sms % 2 == 0 ? 2 : 1);
   g.warps = 20;
   g.xb = 4;
-  g.es = 2;
+  g.es = 3;
   int over[6] = {0, 0, 0, 0, 0, 0};
   if (const char* e = getenv("LOOPSB_TILED_GEOM"))
     sscanf(e, "%d,%d,%d,%d,%d,%d", &over[0], &over[1], &over[2], &over[3], &over[4], &over[5]);
@@ -645,6 +821,7 @@ inline geom choose_geom(int rows, int cols, int sms, int max_smem) {
   if (over[2] > 0) g.warps = over[2];
   if (over[4] > 0) g.xb = over[4];
   if (over[5] > 0) g.es = over[5];
+  if (const char* e = getenv("LOOPSB_TILED_PACK")) g.pack = atoi(e) != 0;
   if (over[0] > 0) {
     g.nb = over[0];
   } else {

@@ -130,11 +130,12 @@ def test_out_of_range_column_is_rejected(lib):
 
 
 def test_powerlaw_sample_of_the_bench_workload(lib, oracle):
-    """A 2^12-row cut of the bench generator through the default-like geometry."""
+    """A 2^12-row cut of the bench generator: padding (step tails, whole
+    prefetch groups) stays a small fraction when streams are tens of steps long."""
     from loops_b200 import generate as g
     rows = cols = 1 << 12
     off, idx, val = g.synth_csr(rows, cols, rows * 32)
     off, idx, val = off.numpy(), idx.numpy(), val.numpy()
     x = g.x_recipe(cols).numpy()
-    img = _check(lib, oracle, rows, cols, off, idx, val, x, (4, 4, 16, 256, 2, 3))
-    assert img["g"]["pad_entries"] < 0.2 * rows * 32
+    img = _check(lib, oracle, rows, cols, off, idx, val, x, (2, 2, 8, 512, 2, 2))
+    assert img["g"]["pad_entries"] < 0.1 * rows * 32

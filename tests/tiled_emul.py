@@ -36,7 +36,7 @@ def build_image(lib, rows, cols, off, idx, val, geometry):
 
     img = {
         "g": g,
-        "steps": arr(ps[0], g["total_steps"] * 256, C.c_uint32, np.uint32).reshape(-1, 256),
+        "steps": arr(ps[0], (g["total_steps"] + g["es"]) * 256, C.c_uint32, np.uint32).reshape(-1, 256),
         "stream_base": arr(ps[1], ns + 1, C.c_int32, np.int64),
         "fs": arr(ps[2], ns * g["nband"], C.c_uint16, np.int64).reshape(ns, g["nband"]),
         "le": arr(ps[3], ns * g["nband"], C.c_uint16, np.int64).reshape(ns, g["nband"]),
@@ -50,7 +50,7 @@ def build_image(lib, rows, cols, off, idx, val, geometry):
 def emulate(img, x, rows, cols):
     """Returns (y, triples) where triples = sorted array of decoded (row, col, value bits)."""
     g = img["g"]
-    nb, q, W, cb, xb = g["nb"], g["q"], g["warps"], g["cb"], g["xb"]
+    nb, q, W, cb, xb, es = g["nb"], g["q"], g["warps"], g["cb"], g["xb"], g["es"]
     rb, rw, cq, nband = g["rb"], g["rw"], g["cq"], g["nband"]
     zero_slot = xb * cb
     blk = img["blk_begin"]
@@ -67,29 +67,50 @@ def emulate(img, x, rows, cols):
             s_id = cta * W + w
             base, end = img["stream_base"][s_id], img["stream_base"][s_id + 1]
             fs, le = img["fs"][s_id], img["le"][s_id]
-            acq = rel = 0
-            resident = [-1] * xb
+            acq = 0
+            resident = [-1] * xb     # band sitting in each ring slot (as this warp sees it)
+            held = []                # bands acquired and not yet released, oldest first
+            done = set()             # bands released
+            assert (end - base) % es == 0, "streams are whole prefetch groups"
+
+            def acquire(keep):
+                nonlocal acq
+                old = resident[acq % xb]
+                assert old < 0 or old in done, ("x ring would deadlock: slot still held", cta, w, acq, old)
+                resident[acq % xb] = acq
+                if keep:
+                    held.append(acq)
+                else:
+                    done.add(acq)
+                acq += 1
+
             for s in range(end - base):
                 words = img["steps"][base + s]
                 ids, vals = words[:128], words[128:].view(np.float32)
-                while acq < nband and fs[acq] <= s:
-                    assert acq - rel < xb, ("x ring would deadlock", cta, w, s, acq, rel)
-                    resident[acq % xb] = acq
-                    acq += 1
-                    while rel < acq and le[rel] <= s:
-                        rel += 1
+                meta = 0
+                for lane in range(32):
+                    meta |= int(ids[4 * lane] >> np.uint32(31)) << lane
+                assert not np.any(ids.reshape(32, 4)[:, 1:] & FLAG), "bit 31 of slots 1..3 must be clear"
+                lead, plen = (meta >> 1) & 0xFFF, (meta >> 13) & 0xF
+                pat, nrel = (meta >> 17) & 0xFF, (meta >> 25) & 0xF
+                for _ in range(lead):
+                    acquire(False)
+                for i in range(plen):
+                    acquire(bool((pat >> i) & 1))
+                # cross-check with the band tables the builder derived the word from
+                assert acq == int(np.sum(fs <= s)), ("acquire count differs from the band table", cta, w, s)
+                rel = 0   # entries may only reference held bands (checked below)
                 lc_enc = (ids & np.uint32(0xFFFF)).astype(np.int64)
                 lr = ((ids >> np.uint32(16)) & np.uint32(0x7FFF)).astype(np.int64)
-                flag = (ids & FLAG) != 0
+                dirty = bool(meta & 1)
                 pad = lr == rb
                 assert np.all(lc_enc[pad] == zero_slot) and np.all(vals[pad] == 0), "bad padding entry"
-                assert not np.any(flag[pad])
                 real = ~pad
                 assert np.all(lc_enc[real] < zero_slot)
                 k = lc_enc // cb
                 band = np.array([resident[int(kk)] if kk < xb else -1 for kk in k])
-                assert np.all(band[real] >= rel), ("entry of a released band", cta, w, s)
                 assert np.all(band[real] >= 0)
+                assert all(int(bb) in held for bb in np.unique(band[real])), ("entry of a band not held", cta, w, s)
                 col = qi * cq + band * cb + (lc_enc - k * cb)
                 row = blk[rbi] + lr
                 assert np.all(col[real] < cols) and np.all(row[real] < rows)
@@ -104,10 +125,8 @@ def emulate(img, x, rows, cols):
                         slots_of.setdefault(int(lr[i]), []).append(i)
                 bad_rows = {r for r, sl in slots_of.items()
                             if sl[-1] - sl[0] + 1 != len(sl) or sl[-1] // 4 - sl[0] // 4 >= 2}
-                for i in range(128):
-                    if not pad[i]:
-                        assert bool(flag[i]) == (int(lr[i]) in bad_rows), ("flag mismatch", cta, w, s, i)
-                if not flag.any():
+                assert dirty == bool(bad_rows), ("dirty bit mismatch", cta, w, s)
+                if not dirty:
                     # clean step, the kernel's order: run sums inside a lane, a run that
                     # started in the previous lane is handed to it, one update per run
                     v = prod.copy()
@@ -136,17 +155,17 @@ def emulate(img, x, rows, cols):
                             if not pad[i]:
                                 ys[lr[i]] = np.float32(ys[lr[i]] + prod[i])
                 out_r.append(row[real]); out_c.append(col[real]); out_v.append(vals[real].view(np.uint32))
-                while rel < acq and le[rel] <= s + 1:
-                    rel += 1
-            nsteps = end - base
+                # bands whose last entry is in this step are released, oldest first
+                assert nrel <= len(held)
+                for _ in range(nrel):
+                    bnd = held.pop(0)
+                    assert le[bnd] == s + 1, ("released a band before its last entry", cta, w, s, bnd)
+                    done.add(bnd)
+                assert all(le[bnd] > s + 1 for bnd in held), ("band kept past its last entry", cta, w, s)
+            assert not held
             while acq < nband:
-                assert fs[acq] <= nsteps
-                assert acq - rel < xb
-                acq += 1
-                while rel < acq:
-                    assert le[rel] <= nsteps
-                    rel += 1
-            assert rel == acq == nband or nband == 0 or rel <= acq
+                acquire(False)
+            assert done == set(range(nband))
         y_parts[qi, blk[rbi]: blk[rbi + 1]] = ys[: blk[rbi + 1] - blk[rbi]]
     y = y_parts[0].copy()
     for qq in range(1, q):

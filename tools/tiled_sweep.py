@@ -32,6 +32,19 @@ def time_ms(fn, warm=5, reps=40):
     return ts[len(ts) // 2], ts[0]
 
 
+def time_b2b_ms(fn, warm=5, reps=100):
+    """Back-to-back launches between one event pair (what bench.py's `value` sees)."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record(); b.synchronize()
+    return a.elapsed_time(b) / reps
+
+
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     small = "--small" in sys.argv
@@ -70,13 +83,15 @@ def main():
         spmv.merge_path_flat(A, x, y, tiled=True)
         ok = bool(torch.equal(y, y0))
         med, best = time_ms(lambda: spmv.merge_path_flat(A, x, y, sync=False, tiled=True))
+        b2b = time_b2b_ms(lambda: spmv.merge_path_flat(A, x, y, sync=False, tiled=True))
         ok2 = bool(torch.equal(y, y0))
         gbs = nbytes / med / 1e6
-        print(f"{geo}: {med*1e3:.1f} us median, {best*1e3:.1f} min, {gbs:.0f} GB/s ({gbs/peak:.3f} of peak) ok={ok and ok2} "
+        print(f"{geo}: {med*1e3:.1f} us median, {best*1e3:.1f} min, back-to-back {b2b*1e3:.1f} us ({nbytes/b2b/1e6/peak:.3f} of peak), "
+              f"{gbs:.0f} GB/s ({gbs/peak:.3f} of peak) ok={ok and ok2} "
               f"geom=({info['nb']},{info['q']},{info['warps']},{info['cb']},{info['xb']},{info['es']}) smem={info['smem_bytes']} "
               f"pad={info['pad_entries']/info['real_entries']:.4f} flagged_steps={info['flagged_steps']/max(info['total_steps'],1):.3f} "
               f"build={build_s:.1f}s", flush=True)
-        out["cells"].append({"geometry": geo, "ms_median": med, "ms_min": best, "gbs": gbs, "frac": gbs / peak,
+        out["cells"].append({"geometry": geo, "ms_median": med, "ms_min": best, "ms_back_to_back": b2b, "gbs": gbs, "frac": gbs / peak,
                              "ok": ok and ok2, "info": info, "build_s": build_s})
         A.drop_plans()
     print(json.dumps(out))
