@@ -200,14 +200,22 @@ void free_probes(loopsb_plan* p) {
 namespace {
 int launch_tiled(bt::plan_data* d, const float* x, float* y, cudaStream_t s) {
   bt::params p;
-  p.steps = d->steps; p.stream_base = d->stream_base; p.blk_begin = d->blk_begin; 
+  p.steps = d->steps; p.steps_end = d->steps + size_t(d->total_steps + d->g.es) * bt::kStepWords; p.stream_base = d->stream_base; p.blk_begin = d->blk_begin; 
   p.x = x; p.y = y; p.partial = d->partial; p.counters = d->counters;
   p.rows = d->g.rows; p.cols = d->g.cols; p.rb = d->g.rb; p.cq = d->g.cq; p.cb = d->g.cb;
   p.xb = d->g.xb; p.es = d->g.es; p.nband = d->g.nband; p.q = d->g.q; p.nb = d->g.nb;
   p.prof = d->prof;
+  p.peers = d->peers;
   bt::kernel_fn k = bt::kernel_for(d->g.warps, d->g.es, d->prof != nullptr);
-  k<<<d->g.grid(), d->g.cta_threads(), d->smem, s>>>(p);
-  LOOPSB_CUDA_TRY(cudaGetLastError());
+  if (d->peers) {
+    // every CTA resident at once (checked at plan time): the CTAs of a row block may wait for each other
+    void* args[] = {&p};
+    LOOPSB_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(k), dim3(d->g.grid()),
+                                                dim3(d->g.cta_threads()), args, size_t(d->smem), s));
+  } else {
+    k<<<d->g.grid(), d->g.cta_threads(), d->smem, s>>>(p);
+    LOOPSB_CUDA_TRY(cudaGetLastError());
+  }
   return LOOPSB_OK;
 }
 
@@ -364,7 +372,7 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const 
       cudaMalloc(&d->stream_base, base_b) != cudaSuccess ||
       cudaMalloc(&d->blk_begin, im.blk_begin.size() * 4) != cudaSuccess ||
       (part_b && cudaMalloc(&d->partial, part_b) != cudaSuccess) ||
-      (part_b && cudaMalloc(&d->counters, size_t(im.g.nb) * 4) != cudaSuccess)) {
+      (part_b && cudaMalloc(&d->counters, size_t(im.g.nb) * 8) != cudaSuccess)) {
     (void)cudaGetLastError();
     set_error("device allocation of the band-tiled copy failed (%zu bytes)", steps_b + part_b);
     return fail(LOOPSB_ERR_ALLOC);
@@ -372,7 +380,7 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const 
   if (cudaMemcpy(d->steps, im.steps.data(), steps_b, cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(d->stream_base, im.stream_base.data(), base_b, cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(d->blk_begin, im.blk_begin.data(), im.blk_begin.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
-      (part_b && cudaMemset(d->counters, 0, size_t(im.g.nb) * 4) != cudaSuccess)) {
+      (part_b && cudaMemset(d->counters, 0, size_t(im.g.nb) * 8) != cudaSuccess)) {
     set_error("upload of the band-tiled copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     return fail(LOOPSB_ERR_CUDA);
   }
@@ -385,6 +393,16 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const 
     set_error("cannot opt in to %d bytes of dynamic shared memory", d->smem);
     (void)cudaGetLastError();
     return fail(LOOPSB_ERR_CUDA);
+  }
+  {
+    // one wave? then the launch can be cooperative and the q CTAs of a row block share the reduction
+    int per_sm = 0, coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, plan->device);
+    if (coop && im.g.q > 1 && !getenv("LOOPSB_TILED_NO_PEERS") &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, im.g.cta_threads(), size_t(d->smem)) == cudaSuccess &&
+        per_sm * dp->sm_count >= im.g.grid())
+      d->peers = 1;
+    (void)cudaGetLastError();
   }
   d->key_indices = col_indices;
   d->key_values = values;

@@ -56,6 +56,7 @@ constexpr int kPerLane = 4;
 constexpr int kStep = kLanes * kPerLane;  // entries per step
 constexpr int kStepWords = 2 * kStep;     // 256 words = 1 KB
 constexpr uint32_t kFlagBit = 0x80000000u;
+constexpr int kL2Ahead = 6;               // steps between the L2 prefetch and the register prefetch
 // Step control word (ballot of bit 31 of the slot-0 ids):
 //   bit 0       dirty: some row of the step cannot be combined by the fast path
 //   bits 1..12  lead : empty bands to acquire and release at once before the step
@@ -458,13 +459,15 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
 // ---------------------------------------------------------------------------
 struct params {
   const uint32_t* steps;
+  const uint32_t* steps_end;  // one past the last word of the step buffer (L2 prefetch guard)
   const int32_t* stream_base;
   const int32_t* blk_begin;   // nb + 1 row-block boundaries
   const float* x;
   float* y;
   float* partial;       // [q][nb*rb] when q > 1
-  unsigned* counters;   // [nb] when q > 1
+  unsigned* counters;   // [2 * nb] when q > 1 (arrivals, departures)
   int rows, cols, rb, cq, cb, xb, es, nband, q, nb;
+  int peers;            // 1: cooperative launch, the q CTAs of a row block share the reduction
   long long* prof;      // PROFILE builds: 8 counters per consumer warp, then 4 wall-clock stamps per CTA
 };
 
@@ -674,6 +677,12 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
         __syncwarp();   // y rows of this step are settled before the next step's loads
         release(int(m >> kMetaRelShift) & 0xf);
         load_step(buf[k], refill, lane);   // step s + DEPTH, into the registers just freed
+        {
+          // pull step s + DEPTH + kAhead from HBM into L2 (eight 128-byte lines, one
+          // per lane 0..7): the register prefetch above then only pays an L2 hit
+          const uint32_t* far = refill + size_t(kL2Ahead) * kStepWords + lane * 32;
+          if (lane < 8 && far < p.steps_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(far));
+        }
         refill += kStepWords;
       }
     }
@@ -700,9 +709,14 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
     for (int i = tid; i < rows_here; i += NT) p.y[row0 + i] = ys[i];
     return;
   }
-  // q > 1: publish this CTA's partial rows; the last of the q CTAs of the row
-  // block to arrive adds the partials in part order and writes y. Partials are
-  // padded to 4 rows per block so they move as 128-bit words.
+  // q > 1: publish this CTA's partial rows, then add the q partials of the row
+  // block in part order. Partials are padded to 4 rows per block so they move as
+  // 128-bit words. Two protocols:
+  //  * peers (cooperative launch, every CTA resident): each of the q CTAs waits
+  //    until all q partials are published and reduces its own 1/q of the rows --
+  //    the reduction is latency-bound (L2 round trips), so four CTAs doing one
+  //    trip each beat one CTA doing them all;
+  //  * last arriver (any grid): the last CTA to publish reduces the whole block.
   const int rb4 = (p.rb + 3) & ~3;
   const size_t pitch = size_t(p.nb) * size_t(rb4);
   const int n4 = (rows_here + 3) >> 2;
@@ -711,32 +725,45 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
   for (int i = tid; i < n4; i += NT) __stcg(mine + i, ys4[i]);
   __threadfence();
   __syncthreads();
-  if (tid == 0) {
-    const unsigned t = atomicAdd(&p.counters[rbi], 1u);
-    *last_flag = (t == unsigned(p.q - 1));
+  int lo = 0, hi = n4;
+  if (p.peers) {
+    if (tid == 0) {
+      atomicAdd(&p.counters[rbi], 1u);
+      volatile unsigned* c = p.counters + rbi;
+      while (*c < unsigned(p.q)) __nanosleep(64);
+    }
+    __syncthreads();
+    const int chunk = (n4 + p.q - 1) / p.q;
+    lo = min(n4, qi * chunk);
+    hi = min(n4, lo + chunk);
+  } else {
+    if (tid == 0) {
+      const unsigned t = atomicAdd(&p.counters[rbi], 1u);
+      *last_flag = (t == unsigned(p.q - 1));
+    }
+    __syncthreads();
+    if (!*last_flag) hi = 0;
   }
-  __syncthreads();
-  if (*last_flag) {
+  if (hi > lo) {
     __threadfence();
     const float4* part = reinterpret_cast<const float4*>(p.partial + size_t(rbi) * rb4);
     const size_t pitch4 = pitch >> 2;
-    // three row groups per thread and trip, all their partial loads issued before
-    // the first add: the reduction is latency-bound (L2 round trips), so the
-    // loads have to be in flight together
+    // three row groups per thread and trip, all their partial loads issued
+    // before the first add, so the L2 round trips overlap
     constexpr int U = 3;
-    for (int i0 = tid; i0 < n4; i0 += NT * U) {
+    for (int i0 = lo + tid; i0 < hi; i0 += NT * U) {
       float4 v[U][4];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int i = i0 + u * NT;
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq)
-          if (qq < p.q && qq != qi && i < n4) v[u][qq] = __ldcg(part + size_t(qq) * pitch4 + i);
+          if (qq < p.q && qq != qi && i < hi) v[u][qq] = __ldcg(part + size_t(qq) * pitch4 + i);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int i = i0 + u * NT;
-        if (i >= n4) break;
+        if (i >= hi) break;
         float4 acc = (qi == 0) ? ys4[i] : v[u][0];
 #pragma unroll
         for (int qq = 1; qq < 4; ++qq)
@@ -752,7 +779,16 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
         if (r + 3 < rows_here) out[3] = acc.w;
       }
     }
-    if (tid == 0) p.counters[rbi] = 0u;  // ready for the next launch
+  }
+  // re-arm the counters for the next launch
+  if (p.peers) {
+    __syncthreads();   // every thread of this CTA has read the peers' partials
+    if (tid == 0) {
+      const unsigned d = atomicAdd(&p.counters[p.nb + rbi], 1u);
+      if (d == unsigned(p.q - 1)) { p.counters[rbi] = 0u; p.counters[p.nb + rbi] = 0u; }
+    }
+  } else if (hi > lo && tid == 0) {
+    p.counters[rbi] = 0u;
   }
   if (PROFILE && stamps) { __syncthreads(); if (boss) stamps[3] = wall_ns(); }
 }
@@ -772,6 +808,7 @@ struct plan_data {
   long long total_steps = 0, real_entries = 0, pad_entries = 0, flagged_entries = 0, flagged_steps = 0;
   long long bytes = 0;
   int smem = 0;
+  int peers = 0;   // the grid fits the device in one wave: launch cooperatively, share the q-way reduction
   long long* prof = nullptr;  // LOOPSB_DEBUG_PHASES: 8 counters per consumer warp
 };
 
