@@ -848,8 +848,10 @@ inline kernel_fn kernel_for(int warps, int depth, bool profile = false) {
 inline geom choose_geom(int rows, int cols, int sms, int max_smem) {
   geom g;
   g.q = (sms % 4 == 0) ? 4 : (sms % 2 == 0 ? 2 : 1);
-  g.warps = 20;
-  g.xb = 4;
+  // measured best on B200 for BASELINE config 2 (tools/tiled_sweep.py, profiles/):
+  // 24 consumer warps, 3 x 7168-column bands in the x ring, 3 steps prefetched
+  g.warps = 24;
+  g.xb = 3;
   g.es = 3;
   int over[6] = {0, 0, 0, 0, 0, 0};
   if (const char* e = getenv("LOOPSB_TILED_GEOM"))
@@ -874,9 +876,9 @@ inline geom choose_geom(int rows, int cols, int sms, int max_smem) {
   if (over[3] > 0) {
     g.cb = over[3];
   } else {
-    // widest band (<= 4096 columns) whose ring still fits beside y and the stream rings
+    // widest band (<= 7168 columns) whose ring still fits beside the y rows
     const int cq = std::max(4, (ceil_div(cols, g.q) + 3) & ~3);
-    int cb = std::min(std::min(kMaxRingFloats / g.xb, 4096), (cq + 63) & ~63) & ~3;
+    int cb = std::min(std::min(kMaxRingFloats / g.xb, 7168), (cq + 63) & ~63) & ~3;
     for (; cb > 64; cb -= 64) {
       geom t = g;
       t.cb = cb;
