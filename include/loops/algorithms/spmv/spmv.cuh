@@ -67,6 +67,51 @@ inline util::timer_t merge_path_flat(csr_t<int, int, float>& csr, vector_t<float
                      detail::raw(csr.indices), nullptr, detail::raw(x), detail::raw(y), csr.rows, csr.cols, stream);
 }
 
+/**
+ * @brief A merge_path_flat plan kept across calls -- what the reference's
+ * `schedule::merge_path::preprocess_t` is to one launch
+ * (schedule/merge_path_flat.hxx:92-172), made re-usable for iterative solvers.
+ * With `band_tiled` (default) the plan also asks the library for a band-tiled
+ * copy of the matrix (loopsb_plan_tile_csr); the library declines when its cost
+ * model prefers the plain CSR kernel, `force` overrides that. The csr_t must
+ * outlive the plan and keep its arrays (the copy is keyed by their addresses).
+ *
+ *     algorithms::spmv::merge_path_plan_t plan(csr);      // once per matrix
+ *     for (...) plan(x, y);                                // every iteration
+ */
+class merge_path_plan_t {
+ public:
+  explicit merge_path_plan_t(csr_t<int, int, float>& csr, cudaStream_t stream = 0, bool band_tiled = true,
+                             bool force = false)
+      : csr_(csr), plan_(csr.layout().descriptor(), LOOPSB_SCHED_MERGE_PATH_FLAT, stream) {
+    if (band_tiled) {
+      const int rc = loopsb_plan_tile_csr(plan_.p, detail::raw(csr.indices), detail::raw(csr.values),
+                                          static_cast<int32_t>(csr.cols), force ? LOOPSB_TILE_FORCE : 0, stream);
+      if (rc != LOOPSB_OK && rc != LOOPSB_ERR_UNSUPPORTED) error::throw_if_status(rc, "loopsb_plan_tile_csr");
+      tiled_ = rc == LOOPSB_OK;
+    }
+  }
+  /// True when SpMV calls on this plan run the band-tiled kernel.
+  bool band_tiled() const { return tiled_; }
+  /// y = A x; synchronous like the reference wrappers, times the SpMV launch only.
+  util::timer_t operator()(vector_t<float>& x, vector_t<float>& y, cudaStream_t stream = 0) {
+    util::timer_t timer(stream);
+    timer.start();
+    error::throw_if_status(
+        loopsb_spmv_f32(plan_.p, detail::raw(csr_.values), detail::raw(csr_.indices), nullptr, detail::raw(x),
+                        detail::raw(y), static_cast<int32_t>(csr_.rows), static_cast<int32_t>(csr_.cols), stream),
+        "loopsb_spmv_f32");
+    cudaStreamSynchronize(stream);
+    timer.stop();
+    return timer;
+  }
+
+ private:
+  csr_t<int, int, float>& csr_;
+  detail::plan_guard plan_;
+  bool tiled_ = false;
+};
+
 inline void work_oriented(csr_t<int, int, float>& csr, vector_t<float>& x, vector_t<float>& y,
                           cudaStream_t stream = 0) {
   detail::run(csr.layout().descriptor(), LOOPSB_SCHED_WORK_ORIENTED, detail::raw(csr.values),

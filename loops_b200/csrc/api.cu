@@ -360,6 +360,13 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const 
   }
   if (rc != LOOPSB_OK) return rc;
   h_idx.clear(); h_idx.shrink_to_fit(); h_val.clear(); h_val.shrink_to_fit();
+  if (!force && im.flagged_steps * 20 > im.total_steps) {
+    // rows with long runs inside a band (or too many bands per step) push steps
+    // onto the general y-update path; above 5 % of the steps the plain kernel wins
+    set_error("band-tiled plan not profitable (%lld of %lld steps need the general y-update path)",
+              im.flagged_steps, im.total_steps);
+    return LOOPSB_ERR_UNSUPPORTED;
+  }
 
   bt::plan_data* d = new (std::nothrow) bt::plan_data();
   if (!d) { set_error("host allocation failed"); return LOOPSB_ERR_ALLOC; }

@@ -127,6 +127,14 @@ int main() {
   try {
     auto t = algorithms::spmv::merge_path_flat(csr, x, y);
     check("algorithms::spmv::merge_path_flat", y, ref);
+    // the re-usable plan with the band-tiled copy (forced: this matrix is below the cost model's size)
+    algorithms::spmv::merge_path_plan_t plan(csr, 0, true, true);
+    for (int rep = 0; rep < 3; ++rep) {
+      thrust::fill(y.begin(), y.end(), -1.0f);
+      plan(x, y);
+    }
+    if (!plan.band_tiled()) { std::printf("FAIL merge_path_plan_t did not tile\n"); ++failures; }
+    check("algorithms::spmv::merge_path_plan_t (band-tiled)", y, ref);
     std::printf("   timer_t: %.3f ms\n", t.milliseconds());
     algorithms::spmv::work_oriented(csr, x, y);   check("algorithms::spmv::work_oriented", y, ref);
     algorithms::spmv::thread_mapped(csr, x, y);   check("algorithms::spmv::thread_mapped", y, ref);
