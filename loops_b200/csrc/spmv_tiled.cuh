@@ -45,7 +45,9 @@
 #include <loops/util/tma.hxx>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
+#include <thread>
 #include <vector>
 
 namespace loopsb {
@@ -127,7 +129,23 @@ struct host_image {
   long long total_steps = 0, real_entries = 0, pad_entries = 0, flagged_entries = 0, flagged_steps = 0;
 };
 
-// Build the image from HOST CSR arrays. Pure host code (unit-tested on CPU).
+// Static split of [0, n) over the host threads (LOOPSB_HOST_THREADS, default
+// min(hardware threads, 16)); fn(begin, end, thread index).
+template <typename F>
+inline void parallel_for(long long n, F fn) {
+  int nt = 0;
+  if (const char* e = getenv("LOOPSB_HOST_THREADS")) nt = atoi(e);
+  if (nt <= 0) nt = int(std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
+  nt = int(std::min<long long>(nt, std::max<long long>(1, n)));
+  if (nt == 1) { fn(0LL, n, 0); return; }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nt; ++t)
+    pool.emplace_back([=]() { fn(n * t / nt, n * (t + 1) / nt, t); });
+  for (auto& th : pool) th.join();
+}
+
+// Build the image from HOST CSR arrays. Pure host code (unit-tested on CPU),
+// every pass split over the host threads by rows, row blocks, streams or steps.
 // Returns LOOPSB_OK / LOOPSB_ERR_UNSUPPORTED / LOOPSB_ERR_INVALID.
 inline int build_host(host_image& im, geom g, int rows, int cols, const int* off, const int* idx,
                       const float* val) {
@@ -137,12 +155,19 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
   const long long nnz = rows > 0 ? off[rows] : 0;
   // ---- pass 0: nonzeros per (row, column part); validates the column ids ----
   std::vector<int32_t> rowpart(size_t(rows) * g.q, 0);
-  for (int r = 0; r < rows; ++r)
-    for (int a = off[r]; a < off[r + 1]; ++a) {
-      const int c = idx[a];
-      if (c < 0 || c >= cols) { set_error("band-tiled plan: column id %d out of range at atom %d", c, a); return LOOPSB_ERR_INVALID; }
-      ++rowpart[size_t(r) * g.q + c / g.cq];
-    }
+  std::atomic<long long> bad_atom(-1);
+  parallel_for(rows, [&](long long r0, long long r1, int) {
+    for (long long r = r0; r < r1; ++r)
+      for (int a = off[r]; a < off[r + 1]; ++a) {
+        const int c = idx[a];
+        if (c < 0 || c >= cols) { bad_atom.store(a); return; }
+        ++rowpart[size_t(r) * g.q + c / g.cq];
+      }
+  });
+  if (bad_atom.load() >= 0) {
+    set_error("band-tiled plan: column id %d out of range at atom %lld", idx[bad_atom.load()], bad_atom.load());
+    return LOOPSB_ERR_INVALID;
+  }
   // ---- row blocks: equal nonzero counts, at most g.rb rows each ----
   const int rb_cap = g.rb;
   im.blk_begin.assign(size_t(g.nb) + 1, 0);
@@ -166,116 +191,127 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
   // counts inside this CTA's column part ----
   im.warp_begin.assign(size_t(g.grid()) * (g.warps + 1), 0);
   std::vector<uint8_t> wmap(size_t(rows) * g.q, 0);   // warp that owns (row, part)
-  int rw_max = 1;
-  for (int rbi = 0; rbi < g.nb; ++rbi) {
-    const int b0 = im.blk_begin[rbi], b1 = im.blk_begin[rbi + 1];
-    for (int qi = 0; qi < g.q; ++qi) {
-      long long tot = 0;
-      for (int r = b0; r < b1; ++r) tot += rowpart[size_t(r) * g.q + qi];
-      int32_t* wb = &im.warp_begin[(size_t(rbi) * g.q + qi) * (g.warps + 1)];
-      long long acc = 0;
-      int w = 0;
-      wb[0] = 0;
-      for (int r = b0; r < b1; ++r) {
-        // row r opens warp w+1 once the rows before it hold w+1 shares of the nonzeros
-        while (w + 1 < g.warps && acc * g.warps >= tot * (w + 1) && tot > 0) wb[++w] = r - b0;
-        wmap[size_t(r) * g.q + qi] = uint8_t(w);
-        acc += rowpart[size_t(r) * g.q + qi];
+  std::vector<int> rw_of_block(size_t(g.nb), 1);
+  parallel_for(g.nb, [&](long long k0, long long k1, int) {
+    for (int rbi = int(k0); rbi < int(k1); ++rbi) {
+      const int b0 = im.blk_begin[rbi], b1 = im.blk_begin[rbi + 1];
+      for (int qi = 0; qi < g.q; ++qi) {
+        long long tot = 0;
+        for (int r = b0; r < b1; ++r) tot += rowpart[size_t(r) * g.q + qi];
+        int32_t* wb = &im.warp_begin[(size_t(rbi) * g.q + qi) * (g.warps + 1)];
+        long long acc = 0;
+        int w = 0;
+        wb[0] = 0;
+        for (int r = b0; r < b1; ++r) {
+          // row r opens warp w+1 once the rows before it hold w+1 shares of the nonzeros
+          while (w + 1 < g.warps && acc * g.warps >= tot * (w + 1) && tot > 0) wb[++w] = r - b0;
+          wmap[size_t(r) * g.q + qi] = uint8_t(w);
+          acc += rowpart[size_t(r) * g.q + qi];
+        }
+        while (w + 1 <= g.warps) wb[++w] = b1 - b0;
+        for (int k = 0; k < g.warps; ++k) rw_of_block[rbi] = std::max(rw_of_block[rbi], wb[k + 1] - wb[k]);
       }
-      while (w + 1 <= g.warps) wb[++w] = b1 - b0;
-      for (int k = 0; k < g.warps; ++k) rw_max = std::max(rw_max, wb[k + 1] - wb[k]);
     }
-  }
-  g.rw = rw_max;
+  });
+  g.rw = *std::max_element(rw_of_block.begin(), rw_of_block.end());
   im.g = g;
-  std::vector<int32_t> count(size_t(ns) * nband, 0);
   // ---- pass 1: entries per (stream, band) ----
-  {
-    int rbi = 0;
-    for (int r = 0; r < rows; ++r) {
-      while (r >= im.blk_begin[rbi + 1]) ++rbi;
+  std::vector<int32_t> count(size_t(ns) * nband, 0);
+  parallel_for(g.nb, [&](long long k0, long long k1, int) {
+    for (int rbi = int(k0); rbi < int(k1); ++rbi) {
       const size_t sb = size_t(rbi) * g.q;
-      for (int a = off[r]; a < off[r + 1]; ++a) {
-        const int c = idx[a];
-        const int qi = c / g.cq, cl = c - qi * g.cq, b = cl / g.cb;
-        const int w = wmap[size_t(r) * g.q + qi];
-        ++count[((sb + qi) * g.warps + w) * nband + b];
-      }
+      for (int r = im.blk_begin[rbi]; r < im.blk_begin[rbi + 1]; ++r)
+        for (int a = off[r]; a < off[r + 1]; ++a) {
+          const int c = idx[a];
+          const int qi = c / g.cq, cl = c - qi * g.cq, b = cl / g.cb;
+          ++count[((sb + qi) * g.warps + wmap[size_t(r) * g.q + qi]) * nband + b];
+        }
     }
-  }
+  });
   // ---- layout: padded start of every band in every stream ----
   std::vector<int32_t> start(size_t(ns) * nband, 0);
+  std::vector<int32_t> steps_of(size_t(ns), 0);
   im.stream_base.assign(size_t(ns) + 1, 0);
   im.fs.assign(size_t(ns) * nband, 0);
   im.le.assign(size_t(ns) * nband, 0);
-  long long total = 0;
-  for (int s = 0; s < ns; ++s) {
-    long long pos = 0;
-    int step_min_band = -1;  // smallest band with an entry in the step that holds `pos`
-    const int32_t* cnt = &count[size_t(s) * nband];
-    int32_t* st = &start[size_t(s) * nband];
+  std::atomic<long long> too_long(0);
+  parallel_for(ns, [&](long long s0, long long s1, int) {
     std::vector<long long> end(nband, 0);
-    for (int b = 0; b < nband; ++b) {
-      if (cnt[b] == 0) { st[b] = int32_t(pos); end[b] = pos; continue; }
-      if (pos % kStep != 0 && b > step_min_band + g.xb - 1) pos = (pos + kStep - 1) / kStep * kStep;
-      if (pos % kStep == 0) step_min_band = b;
-      st[b] = int32_t(pos);
-      const long long e = pos + cnt[b];
-      if ((e - 1) / kStep > pos / kStep) step_min_band = b;  // the step `e` lands in started inside band b
-      pos = e;
-      end[b] = e;
-    }
-    long long nsteps = (pos + kStep - 1) / kStep;
-    nsteps = (nsteps + g.es - 1) / g.es * g.es;   // whole prefetch groups (all-padding steps at the end)
-    if (nsteps > 65535) { set_error("band-tiled plan: a warp stream needs %lld steps (> 65535)", nsteps); return LOOPSB_ERR_UNSUPPORTED; }
-    // band tables: empty bands borrow the first step of the next non-empty one
-    int next_fs = int(nsteps);
-    for (int b = nband - 1; b >= 0; --b) {
-      uint16_t& f = im.fs[size_t(s) * nband + b];
-      uint16_t& l = im.le[size_t(s) * nband + b];
-      if (cnt[b] > 0) {
-        next_fs = int(st[b] / kStep);
-        f = uint16_t(next_fs);
-        l = uint16_t((end[b] - 1) / kStep + 1);
-      } else {
-        f = uint16_t(next_fs);
-        l = uint16_t(next_fs);
+    for (long long s = s0; s < s1; ++s) {
+      long long pos = 0;
+      int step_min_band = -1;  // smallest band with an entry in the step that holds `pos`
+      const int32_t* cnt = &count[size_t(s) * nband];
+      int32_t* st = &start[size_t(s) * nband];
+      for (int b = 0; b < nband; ++b) {
+        if (cnt[b] == 0) { st[b] = int32_t(pos); end[b] = pos; continue; }
+        if (pos % kStep != 0 && b > step_min_band + g.xb - 1) pos = (pos + kStep - 1) / kStep * kStep;
+        if (pos % kStep == 0) step_min_band = b;
+        st[b] = int32_t(pos);
+        const long long e = pos + cnt[b];
+        if ((e - 1) / kStep > pos / kStep) step_min_band = b;  // the step `e` lands in started inside band b
+        pos = e;
+        end[b] = e;
       }
+      long long nsteps = (pos + kStep - 1) / kStep;
+      nsteps = (nsteps + g.es - 1) / g.es * g.es;   // whole prefetch groups (all-padding steps at the end)
+      if (nsteps > 65535) { too_long.store(nsteps); nsteps = 0; }
+      // band tables: empty bands borrow the first step of the next non-empty one
+      int next_fs = int(nsteps);
+      for (int b = nband - 1; b >= 0; --b) {
+        uint16_t& f = im.fs[size_t(s) * nband + b];
+        uint16_t& l = im.le[size_t(s) * nband + b];
+        if (cnt[b] > 0) {
+          next_fs = int(st[b] / kStep);
+          f = uint16_t(next_fs);
+          l = uint16_t((end[b] - 1) / kStep + 1);
+        } else {
+          f = uint16_t(next_fs);
+          l = uint16_t(next_fs);
+        }
+      }
+      steps_of[size_t(s)] = int32_t(nsteps);
     }
-    im.stream_base[s] = int32_t(total);
-    total += nsteps;
+  });
+  if (too_long.load() > 0) {
+    set_error("band-tiled plan: a warp stream needs %lld steps (> 65535)", too_long.load());
+    return LOOPSB_ERR_UNSUPPORTED;
   }
+  long long total = 0;
+  for (int s = 0; s < ns; ++s) { im.stream_base[s] = int32_t(total); total += steps_of[s]; }
   im.stream_base[ns] = int32_t(total);
-  if (total > 0x7fffffffLL) { set_error("band-tiled plan: too many steps"); return LOOPSB_ERR_UNSUPPORTED; }
+  if (total > 0x7fffffffLL / 2) { set_error("band-tiled plan: too many steps"); return LOOPSB_ERR_UNSUPPORTED; }
   im.total_steps = total;
   // ---- pass 2: scatter (padding pre-filled) ----
   const uint32_t pad_id = (uint32_t(g.rb) << 16) | uint32_t(g.zero_slot());
-  im.steps.assign(size_t(total + g.es) * kStepWords, 0u);   // + es steps the last prefetch may touch
-  for (long long s = 0; s < total + g.es; ++s) {
-    uint32_t* w = &im.steps[size_t(s) * kStepWords];
-    for (int i = 0; i < kStep; ++i) w[i] = pad_id;
-  }
+  im.steps.resize(size_t(total + g.es) * kStepWords);   // + es steps the last prefetch may touch
+  parallel_for(total + g.es, [&](long long s0, long long s1, int) {
+    for (long long s = s0; s < s1; ++s) {
+      uint32_t* w = &im.steps[size_t(s) * kStepWords];
+      for (int i = 0; i < kStep; ++i) w[i] = pad_id;
+      for (int i = kStep; i < kStepWords; ++i) w[i] = 0u;
+    }
+  });
   std::vector<int32_t>& cursor = start;  // consumed in place
-  {
-    int rbi = 0;
-    for (int r = 0; r < rows; ++r) {
-      while (r >= im.blk_begin[rbi + 1]) ++rbi;
-      const int lr = r - im.blk_begin[rbi];
+  parallel_for(g.nb, [&](long long k0, long long k1, int) {
+    for (int rbi = int(k0); rbi < int(k1); ++rbi) {
       const size_t sb = size_t(rbi) * g.q;
-      for (int a = off[r]; a < off[r + 1]; ++a) {
-        const int c = idx[a];
-        const int qi = c / g.cq, cl = c - qi * g.cq, b = cl / g.cb, lc = cl - b * g.cb;
-        const size_t stream = (sb + qi) * g.warps + wmap[size_t(r) * g.q + qi];
-        const int32_t p = cursor[stream * nband + b]++;
-        uint32_t* sw = &im.steps[(size_t(im.stream_base[stream]) + size_t(p / kStep)) * kStepWords];
-        const int slot = p % kStep;  // lane*4 + j
-        sw[slot] = (uint32_t(lr) << 16) | uint32_t((b % g.xb) * g.cb + lc);
-        float v = val[a];
-        uint32_t vb; memcpy(&vb, &v, 4);
-        sw[kStep + slot] = vb;
+      for (int r = im.blk_begin[rbi]; r < im.blk_begin[rbi + 1]; ++r) {
+        const int lr = r - im.blk_begin[rbi];
+        for (int a = off[r]; a < off[r + 1]; ++a) {
+          const int c = idx[a];
+          const int qi = c / g.cq, cl = c - qi * g.cq, b = cl / g.cb, lc = cl - b * g.cb;
+          const size_t stream = (sb + qi) * g.warps + wmap[size_t(r) * g.q + qi];
+          const int32_t p = cursor[stream * nband + b]++;
+          uint32_t* sw = &im.steps[(size_t(im.stream_base[stream]) + size_t(p / kStep)) * kStepWords];
+          const int slot = p % kStep;  // lane*4 + j
+          sw[slot] = (uint32_t(lr) << 16) | uint32_t((b % g.xb) * g.cb + lc);
+          float v = val[a];
+          uint32_t vb; memcpy(&vb, &v, 4);
+          sw[kStep + slot] = vb;
+        }
       }
     }
-  }
+  });
   im.real_entries = nnz;
   im.pad_entries = total * kStep - nnz;
   // ---- pass 2b: pack every step for the shared-memory banks. Which of the 128
@@ -284,21 +320,20 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
   // slot j over distinct banks of the x ring (bank = ring position mod 32) and of
   // the y rows (bank = row mod 32, counted for the cell that closes the run):
   // an instruction over 32 random banks costs ~3.4 shared-memory wavefronts, a
-  // packed one ~2. All entries of a row inside the step become ONE run (also when
-  // they come from two bands), longest runs are placed first, single entries go
-  // to the slot column where their two banks are least used. ----
-  if (g.pack) {
+  // packed one ~2.2. All entries of a row inside the step become ONE run (also
+  // when they come from two bands), longest runs are placed first, single
+  // entries go to the slot column where their two banks are least used. ----
+  if (g.pack) parallel_for(total, [&](long long step0, long long step1, int) {
     struct ent { uint32_t id, val; };
     std::vector<int64_t> stamp(size_t(g.rb) + 1, -1);
     std::vector<int32_t> unit_of(size_t(g.rb) + 1, 0);
     std::vector<ent> in(kStep), out(kStep);
     std::vector<int> unit_start, unit_len, order;
     std::vector<ent> unit_ents;
-    const uint32_t pad_id2 = (uint32_t(g.rb) << 16) | uint32_t(g.zero_slot());
-    for (long long s = 0; s < total; ++s) {
+    for (long long s = step0; s < step1; ++s) {
       uint32_t* w = &im.steps[size_t(s) * kStepWords];
       // gather units (all entries of one row), preserving the stream order inside a unit
-      unit_start.clear(); unit_len.clear();
+      unit_len.clear();
       int nreal = 0;
       for (int p = 0; p < kStep; ++p) {
         in[p] = ent{w[p], w[kStep + p]};
@@ -313,15 +348,12 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
       unit_start.assign(nu + 1, 0);
       for (int u = 0; u < nu; ++u) unit_start[u + 1] = unit_start[u] + unit_len[u];
       unit_ents.resize(nreal);
-      {
-        std::vector<int>& fill = order;   // reuse as per-unit cursor
-        fill.assign(nu, 0);
-        for (int p = 0; p < kStep; ++p) {
-          const int lr = int((in[p].id >> 16) & 0x7fff);
-          if (lr == g.rb) continue;
-          const int u = unit_of[lr];
-          unit_ents[unit_start[u] + fill[u]++] = in[p];
-        }
+      order.assign(nu, 0);   // per-unit fill cursor first
+      for (int p = 0; p < kStep; ++p) {
+        const int lr = int((in[p].id >> 16) & 0x7fff);
+        if (lr == g.rb) continue;
+        const int u = unit_of[lr];
+        unit_ents[unit_start[u] + order[u]++] = in[p];
       }
       // units by decreasing length (counting sort on min(len, 9))
       order.clear();
@@ -331,7 +363,7 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
       bool used[kLanes][kPerLane] = {};
       int free_in_col[kPerLane] = {kLanes, kLanes, kLanes, kLanes};
       int cx[kPerLane][32] = {}, cy[kPerLane][32] = {};
-      for (int p = 0; p < kStep; ++p) out[p] = ent{pad_id2, 0u};
+      for (int p = 0; p < kStep; ++p) out[p] = ent{pad_id, 0u};
       auto xbank = [](const ent& e) { return int(e.id & 31u); };
       auto ybank = [](const ent& e) { return int((e.id >> 16) & 31u); };
       auto put = [&](int lane, int j, const ent& e, bool closes) {
@@ -385,7 +417,7 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
       if (failed) continue;   // keep the stream order for this step (always a legal layout)
       for (int p = 0; p < kStep; ++p) { w[p] = out[p].id; w[kStep + p] = out[p].val; }
     }
-  }
+  });
   // ---- pass 3: control words. A step is "clean" when every row it touches sits
   // in ONE contiguous range of cells (cell = lane*4 + j) that spans at most two
   // adjacent lanes -- what the kernel's fast path can combine with a per-lane run
@@ -393,11 +425,13 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
   // general path. The x-ring events of the step (which bands the warp must wait
   // for before it, which it is done with after it) come from the band tables. ----
   std::vector<uint32_t> meta(size_t(total), 0u);
-  {
+  std::atomic<long long> flagged_entries(0), flagged_steps(0);
+  parallel_for(total, [&](long long step0, long long step1, int) {
     std::vector<int64_t> stamp(size_t(g.rb) + 1, -1);
     std::vector<int32_t> first(size_t(g.rb) + 1, 0), last(size_t(g.rb) + 1, 0), cnt(size_t(g.rb) + 1, 0);
-    for (long long s = 0; s < total; ++s) {
-      uint32_t* w = &im.steps[size_t(s) * kStepWords];
+    long long fe = 0, fst = 0;
+    for (long long s = step0; s < step1; ++s) {
+      const uint32_t* w = &im.steps[size_t(s) * kStepWords];
       for (int p = 0; p < kStep; ++p) {
         const int lr = int((w[p] >> 16) & 0x7fff);
         if (lr == g.rb) continue;  // padding -> scratch row, harmless
@@ -410,47 +444,57 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
         if (lr == g.rb) continue;
         const bool bad = (last[lr] - first[lr] + 1 != cnt[lr]) ||
                          (last[lr] / kPerLane - first[lr] / kPerLane >= 2);
-        if (bad) { ++im.flagged_entries; any = true; }
+        if (bad) { ++fe; any = true; }
       }
-      if (any) { ++im.flagged_steps; meta[size_t(s)] |= 1u; }
+      if (any) { ++fst; meta[size_t(s)] |= 1u; }
     }
-  }
-  for (int st = 0; st < ns; ++st) {
-    const long long base = im.stream_base[st];
-    const int nsteps = im.stream_base[st + 1] - im.stream_base[st];
-    const int32_t* cnt = &count[size_t(st) * nband];
-    const uint16_t* fs = &im.fs[size_t(st) * nband];
-    const uint16_t* le = &im.le[size_t(st) * nband];
-    int b = 0;
-    while (b < nband) {
-      const int step = fs[b];
-      if (step >= nsteps) break;   // trailing empty bands: acquired and released after the last step
-      // bands b .. e-1 all start (or, being empty, are borrowed) at `step`
-      int e = b;
-      while (e < nband && fs[e] == step) ++e;
-      int lead = 0;
-      while (b + lead < e && cnt[b + lead] == 0) ++lead;
-      const int plen = e - (b + lead);
-      if (lead >= (1 << kMetaLeadBits) || plen > 8) {
-        set_error("band-tiled plan: %d empty / %d starting bands in one step exceed the control word", lead, plen);
-        return LOOPSB_ERR_UNSUPPORTED;
+    flagged_entries += fe;
+    flagged_steps += fst;
+  });
+  im.flagged_entries = flagged_entries.load();
+  im.flagged_steps = flagged_steps.load();
+  std::atomic<int> meta_overflow(0);
+  parallel_for(ns, [&](long long st0, long long st1, int) {
+    for (long long st = st0; st < st1; ++st) {
+      const long long base = im.stream_base[st];
+      const int nsteps = im.stream_base[st + 1] - im.stream_base[st];
+      const int32_t* cnt = &count[size_t(st) * nband];
+      const uint16_t* fs = &im.fs[size_t(st) * nband];
+      const uint16_t* le = &im.le[size_t(st) * nband];
+      int b = 0;
+      while (b < nband) {
+        const int step = fs[b];
+        if (step >= nsteps) break;   // trailing empty bands: acquired and released after the last step
+        // bands b .. e-1 all start (or, being empty, are borrowed) at `step`
+        int e = b;
+        while (e < nband && fs[e] == step) ++e;
+        int lead = 0;
+        while (b + lead < e && cnt[b + lead] == 0) ++lead;
+        const int plen = e - (b + lead);
+        if (lead >= (1 << kMetaLeadBits) || plen > 8) { meta_overflow.store(1); break; }
+        uint32_t pat = 0;
+        for (int i = 0; i < plen; ++i)
+          if (cnt[b + lead + i] > 0) pat |= 1u << i;
+        meta[size_t(base + step)] |= (uint32_t(lead) << kMetaLeadShift) | (uint32_t(plen) << kMetaPlenShift) |
+                                     (pat << kMetaPatShift);
+        b = e;
       }
-      uint32_t pat = 0;
-      for (int i = 0; i < plen; ++i)
-        if (cnt[b + lead + i] > 0) pat |= 1u << i;
-      meta[size_t(base + step)] |= (uint32_t(lead) << kMetaLeadShift) | (uint32_t(plen) << kMetaPlenShift) |
-                                   (pat << kMetaPatShift);
-      b = e;
+      for (int bb = 0; bb < nband; ++bb)
+        if (cnt[bb] > 0) meta[size_t(base + le[bb] - 1)] += 1u << kMetaRelShift;   // nrel <= xb <= 8 by the window rule
     }
-    for (int bb = 0; bb < nband; ++bb)
-      if (cnt[bb] > 0) meta[size_t(base + le[bb] - 1)] += 1u << kMetaRelShift;   // nrel <= xb <= 8 by the window rule
+  });
+  if (meta_overflow.load()) {
+    set_error("band-tiled plan: too many empty / starting bands in one step for the control word");
+    return LOOPSB_ERR_UNSUPPORTED;
   }
-  for (long long s = 0; s < total; ++s) {
-    uint32_t* w = &im.steps[size_t(s) * kStepWords];
-    const uint32_t m = meta[size_t(s)];
-    for (int lane = 0; lane < kLanes; ++lane)
-      if ((m >> lane) & 1u) w[lane * kPerLane] |= kFlagBit;
-  }
+  parallel_for(total, [&](long long step0, long long step1, int) {
+    for (long long s = step0; s < step1; ++s) {
+      uint32_t* w = &im.steps[size_t(s) * kStepWords];
+      const uint32_t m = meta[size_t(s)];
+      for (int lane = 0; lane < kLanes; ++lane)
+        if ((m >> lane) & 1u) w[lane * kPerLane] |= kFlagBit;
+    }
+  });
   return LOOPSB_OK;
 }
 
