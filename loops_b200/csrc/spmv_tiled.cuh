@@ -720,10 +720,13 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
         if (PROFILE) t_rmw += clock64() - t0;
         __syncwarp();   // y rows of this step are settled before the next step's loads
         release(int(m >> kMetaRelShift) & 0xf);
-        load_step(buf[k], refill, lane);   // step s + DEPTH, into the registers just freed
+        // step s + DEPTH into the registers just freed, and step s + DEPTH + kL2Ahead
+        // from HBM into L2 (eight 128-byte lines, one per lane 0..7) so that the
+        // register prefetch only pays an L2 hit. (Stopping both at the end of the
+        // warp's own stream was measured: ~3 % slower than letting them run a few
+        // steps into the neighbour's stream -- the compares cost more than the loads.)
+        load_step(buf[k], refill, lane);
         {
-          // pull step s + DEPTH + kAhead from HBM into L2 (eight 128-byte lines, one
-          // per lane 0..7): the register prefetch above then only pays an L2 hit
           const uint32_t* far = refill + size_t(kL2Ahead) * kStepWords + lane * 32;
           if (lane < 8 && far < p.steps_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(far));
         }
