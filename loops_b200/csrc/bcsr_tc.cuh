@@ -57,6 +57,7 @@ struct plan_data {
   int4* split = nullptr;      // {group, first partial slot, number of chunks, 0}
   float* partial = nullptr;   // [slots][128] fp32
   int sm_count = 0;
+  int ctas_per_sm = 0;        // persistent grid = resident CTAs per SM x SMs
   long long bytes = 0;
 };
 
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(kThreads)
   const uint32_t tmem = sm.tmem_base;
   constexpr uint32_t idesc = make_idesc(128, 32);
 
-  uint32_t uses[2] = {0u, 0u};  // completed-or-pending commits per buffer (same in every thread)
+  uint32_t t = 0;  // K-steps staged so far by this CTA: step t uses buffer t & 1, whose previous use was step t - 2
 
   for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
     const int4 item = __ldg(items + it);
@@ -246,29 +247,40 @@ __global__ void __launch_bounds__(kThreads)
     // [item.y, item.z)
     const int steps = item.z - item.y;
 
-    for (int s = item.y; s < item.z; ++s) {
-      const int buf = s & 1;
-      const int k = 4 * s + slot;
-      uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-      uint2 xs = make_uint2(0, 0);
-      if (k < len) {
+    // Three register stages per thread, two K-steps of look-ahead: while step s
+    // is staged and multiplied, the x slice of step s+1 is in flight (its block
+    // column arrived one step ago) and the block column + values of step s+2
+    // are requested. Without it every K-step paid two dependent memory round
+    // trips (column id -> x) behind a __syncthreads.
+    struct stage_regs { uint4 v0, v1; uint2 xs; int bc; bool valid; };
+    stage_regs st[3];
+    auto load_cv = [&](stage_regs& r, int step) {
+      const int k = 4 * step + slot;
+      r.valid = k < len;
+      r.v0 = make_uint4(0, 0, 0, 0); r.v1 = r.v0; r.xs = make_uint2(0, 0); r.bc = 0;
+      if (r.valid) {
         const long long blk = (long long)start + k;
-        const int bc = __ldg(block_cols + blk);
+        r.bc = __ldg(block_cols + blk);
         const uint4* vp = reinterpret_cast<const uint4*>(values + blk * 16);
-        v0 = __ldg(vp);
-        v1 = __ldg(vp + 1);
-        xs = __ldg(reinterpret_cast<const uint2*>(x + (long long)bc * 4));
+        r.v0 = __ldg(vp);
+        r.v1 = __ldg(vp + 1);
       }
-      // the MMA that last read this buffer must have completed
-      if (uses[buf] > 0)
-        loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.mma_done[buf]), (uses[buf] - 1) & 1u);
+    };
+    auto load_x = [&](stage_regs& r) {
+      if (r.valid) r.xs = __ldg(reinterpret_cast<const uint2*>(x + (long long)r.bc * 4));
+    };
+    auto process = [&](const stage_regs& r, int s) {
+      const uint32_t buf = t & 1u;
+      // the MMA that last read this buffer (step t - 2, its (t/2 - 1)-th use) must have completed
+      if (t >= 2u)
+        loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.mma_done[buf]), ((t >> 1) - 1u) & 1u);
       unsigned char* A = sm.a[buf];
       unsigned char* B = sm.b[buf];
-      *reinterpret_cast<uint2*>(A + tile_offset(4 * b + 0, slot)) = make_uint2(v0.x, v0.y);
-      *reinterpret_cast<uint2*>(A + tile_offset(4 * b + 1, slot)) = make_uint2(v0.z, v0.w);
-      *reinterpret_cast<uint2*>(A + tile_offset(4 * b + 2, slot)) = make_uint2(v1.x, v1.y);
-      *reinterpret_cast<uint2*>(A + tile_offset(4 * b + 3, slot)) = make_uint2(v1.z, v1.w);
-      *reinterpret_cast<uint2*>(B + tile_offset(b, slot)) = xs;
+      *reinterpret_cast<uint2*>(A + tile_offset(4 * b + 0, slot)) = make_uint2(r.v0.x, r.v0.y);
+      *reinterpret_cast<uint2*>(A + tile_offset(4 * b + 1, slot)) = make_uint2(r.v0.z, r.v0.w);
+      *reinterpret_cast<uint2*>(A + tile_offset(4 * b + 2, slot)) = make_uint2(r.v1.x, r.v1.y);
+      *reinterpret_cast<uint2*>(A + tile_offset(4 * b + 3, slot)) = make_uint2(r.v1.z, r.v1.w);
+      *reinterpret_cast<uint2*>(B + tile_offset(b, slot)) = r.xs;
       loops::tma::fence_proxy_async();   // generic-proxy smem writes -> tensor-core (async) proxy
       tc_fence_before_sync();
       __syncthreads();
@@ -277,13 +289,29 @@ __global__ void __launch_bounds__(kThreads)
         umma_bf16(tmem, make_smem_desc(A, 128, 256), make_smem_desc(B, 128, 256), idesc, s > item.y ? 1u : 0u);
         umma_commit(reinterpret_cast<uint64_t*>(&sm.mma_done[buf]));
       }
-      uses[buf] += 1;
+      ++t;
+    };
+    if (steps > 0) {
+      int s = item.y;
+      load_cv(st[0], s);
+      if (s + 1 < item.z) load_cv(st[1], s + 1);
+      load_x(st[0]);
+#define LOOPSB_BCSR_STEP(A_, B_, C_)                       \
+      if (s + 1 < item.z) load_x(st[B_]);                  \
+      if (s + 2 < item.z) load_cv(st[C_], s + 2);          \
+      process(st[A_], s);
+      while (true) {
+        LOOPSB_BCSR_STEP(0, 1, 2) if (++s >= item.z) break;
+        LOOPSB_BCSR_STEP(1, 2, 0) if (++s >= item.z) break;
+        LOOPSB_BCSR_STEP(2, 0, 1) if (++s >= item.z) break;
+      }
+#undef LOOPSB_BCSR_STEP
     }
 
     if (steps > 0) {
       // accumulator complete when the last commit lands
-      const int last = (item.z - 1) & 1;
-      loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.mma_done[last]), (uses[last] - 1) & 1u);
+      const uint32_t last = (t - 1u) & 1u;
+      loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.mma_done[last]), ((t - 1u) >> 1) & 1u);
       // the other buffer's commit (if any) was issued earlier, so it has landed too
       tc_fence_after_sync();
       // lane l of warp w holds scalar row m = 32w + l; its block-row slot is
@@ -347,7 +375,19 @@ inline int run(plan_data* p, const loopsb_layout_t* lay, const uint16_t* values,
   LOOPSB_REQUIRE(lay->num_atoms == 0 || (values && block_cols && x), "null matrix / x pointer");
   LOOPSB_REQUIRE((reinterpret_cast<uintptr_t>(values) & 15u) == 0 && (reinterpret_cast<uintptr_t>(x) & 7u) == 0,
                  "values must be 16-byte and x 8-byte aligned");
-  int grid = p->sm_count * 8;
+  if (p->ctas_per_sm == 0) {
+    // persistent grid: 8 CTAs per SM measured best on B200 (tools/bcsr_bench.py: 6 -> 137 us,
+    // 8 -> 130 us, 10 -> 147 us, 12 -> 139 us); never more than the registers allow
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_bcsr4x4_bf16_kernel, kThreads, 0) != cudaSuccess ||
+        per_sm < 1)
+      per_sm = 8;
+    (void)cudaGetLastError();
+    per_sm = per_sm < 8 ? per_sm : 8;
+    if (const char* e = getenv("LOOPSB_BCSR_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
+    p->ctas_per_sm = per_sm;
+  }
+  int grid = p->sm_count * p->ctas_per_sm;
   if (grid > p->num_items) grid = p->num_items;
   spmv_bcsr4x4_bf16_kernel<<<grid, kThreads, 0, stream>>>(lay->offsets, block_cols, values, x, y, p->order,
                                                         p->num_block_rows, p->items, p->num_items, p->partial,
