@@ -53,6 +53,7 @@ struct plan_data {
   // that a 1024-block row does not serialise inside one CTA.
   int num_items = 0;
   int4* items = nullptr;      // {group, first step, past-last step, partial slot or -1}
+  int4* item_rows = nullptr;  // [item][32 block-row slots] {first block, blocks, block-row id or -1, 0}
   int num_split = 0;
   int4* split = nullptr;      // {group, first partial slot, number of chunks, 0}
   float* partial = nullptr;   // [slots][128] fp32
@@ -67,11 +68,30 @@ __global__ void row_lengths_kernel(const int* __restrict__ off, int n,
   if (r < n) { len[r] = off[r + 1] - off[r]; id[r] = r; }
 }
 
+// One int4 per (work item, block-row slot): what a thread needs to start on an
+// item, in ONE load whose address depends only on the item number -- so it can be
+// requested an item ahead instead of walking items -> order -> offsets.
+__global__ void item_rows_kernel(const int4* __restrict__ items, int num_items, const int* __restrict__ order,
+                                 const int* __restrict__ off, int num_block_rows, int4* __restrict__ out) {
+  const int it = blockIdx.x, b = threadIdx.x;
+  if (it >= num_items) return;
+  const int slot_row = items[it].x * 32 + b;
+  int4 v = make_int4(0, 0, -1, 0);
+  if (slot_row < num_block_rows) {
+    const int r = order[slot_row];
+    v.x = off[r];
+    v.y = off[r + 1] - v.x;
+    v.z = r;
+  }
+  out[(long long)it * 32 + b] = v;
+}
+
 inline void destroy(plan_data* p) {
   if (!p) return;
   if (p->order) cudaFree(p->order);
   if (p->lengths) cudaFree(p->lengths);
   if (p->items) cudaFree(p->items);
+  if (p->item_rows) cudaFree(p->item_rows);
   if (p->split) cudaFree(p->split);
   if (p->partial) cudaFree(p->partial);
   delete p;
@@ -136,6 +156,9 @@ inline int create(plan_data** out, const loopsb_layout_t* lay, int sm_count,
   if (cudaMalloc(&p->items, items.size() * sizeof(int4)) != cudaSuccess) return fail("cudaMalloc(items)");
   if (cudaMemcpy(p->items, items.data(), items.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess)
     return fail("cudaMemcpy(items)");
+  if (cudaMalloc(&p->item_rows, (items.size() + 1) * 32 * sizeof(int4)) != cudaSuccess) return fail("cudaMalloc(item_rows)");
+  item_rows_kernel<<<p->num_items, 32, 0, stream>>>(p->items, p->num_items, p->order, lay->offsets, n, p->item_rows);
+  if (cudaStreamSynchronize(stream) != cudaSuccess) return fail("item_rows_kernel");
   if (!split.empty()) {
     if (cudaMalloc(&p->split, split.size() * sizeof(int4)) != cudaSuccess ||
         cudaMalloc(&p->partial, size_t(slots) * 128 * sizeof(float)) != cudaSuccess)
@@ -143,7 +166,7 @@ inline int create(plan_data** out, const loopsb_layout_t* lay, int sm_count,
     if (cudaMemcpy(p->split, split.data(), split.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess)
       return fail("cudaMemcpy(split)");
   }
-  p->bytes = (long long)n * 8 + (long long)items.size() * 16 + (long long)split.size() * 16 + (long long)slots * 512;
+  p->bytes = (long long)n * 8 + (long long)items.size() * (16 + 512) + (long long)split.size() * 16 + (long long)slots * 512;
   *out = p;
   return LOOPSB_OK;
 }
@@ -216,7 +239,7 @@ __global__ void __launch_bounds__(kThreads)
                              const uint16_t* __restrict__ values, const uint16_t* __restrict__ x,
                              float* __restrict__ y, const int* __restrict__ order, int num_block_rows,
                              const int4* __restrict__ items, int num_items, float* __restrict__ partial,
-                             int num_rows) {
+                             int num_rows, const int4* __restrict__ item_rows) {
   __shared__ tc_shared sm;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -237,33 +260,55 @@ __global__ void __launch_bounds__(kThreads)
   uint32_t t = 0;  // K-steps staged so far by this CTA: step t uses buffer t & 1, whose previous use was step t - 2
 
   for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+    // Both descriptors of the NEXT item go to L2 now (their addresses depend only on
+    // the item number), so the two loads below hit L2 one item later. (Carrying
+    // them in registers was tried: the item fields are warp-uniform, ptxas moves
+    // them to uniform registers right behind the load and the prefetch turns
+    // synchronous.)
+    if (it + int(gridDim.x) < num_items && lane == 0) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(items + it + gridDim.x));
+      if (warp < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(item_rows + (long long)(it + gridDim.x) * 32 + 8 * warp));
+    }
     const int4 item = __ldg(items + it);
-    const int g = item.x;
-    const int slot_row = g * kGroupRows + b;
-    const int r = slot_row < num_block_rows ? __ldg(order + slot_row) : -1;
-    int start = 0, len = 0;
-    if (r >= 0) { start = __ldg(block_offsets + r); len = __ldg(block_offsets + r + 1) - start; }
+    const int4 row = __ldg(item_rows + (long long)it * 32 + b);
+    const int start = row.x, len = row.y;
     // rows are sorted by length; the plan cut the longest row's K loop into
     // [item.y, item.z)
     const int steps = item.z - item.y;
 
-    // Three register stages per thread, two K-steps of look-ahead: while step s
-    // is staged and multiplied, the x slice of step s+1 is in flight (its block
-    // column arrived one step ago) and the block column + values of step s+2
-    // are requested. Without it every K-step paid two dependent memory round
-    // trips (column id -> x) behind a __syncthreads.
-    struct stage_regs { uint4 v0, v1; uint2 xs; int bc; bool valid; };
+    // Two thread->data maps per K-step (tid = 4*b + slot):
+    //  * B tile (x slices) and block columns: thread (b, slot) owns block 4s+slot of
+    //    block-row slot b -- its 8-byte x slice lands conflict-free in the B tile;
+    //  * A tile (values): in round j = 0..3 a warp moves the blocks of TWO block-row
+    //    slots (8w + 2j + lane/16), lane -> (slot_a = (lane/4)%4, row i = lane%4):
+    //    one coalesced 256-byte load (32 lanes x 8 B, every sector fully used) and one
+    //    conflict-free 256-byte shared store into the canonical UMMA layout per
+    //    round. (One thread per whole block -- 2 x LDG.128 and 4 strided 8-byte
+    //    stores -- cost 8-way bank conflicts and half-used sectors.)
+    // Three register stages, two K-steps of look-ahead: while step s is staged and
+    // multiplied, the x slice of step s+1 is in flight (its block column arrived one
+    // step ago) and the column + values of step s+2 are requested.
+    const int slot_a = (lane >> 2) & 3, row_i = lane & 3;
+    int a_start[4], a_len[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int src_lane = 4 * (2 * j + (lane >> 4));   // a lane whose b is the block-row slot of round j
+      a_start[j] = __shfl_sync(0xffffffffu, start, src_lane);
+      a_len[j] = __shfl_sync(0xffffffffu, len, src_lane);
+    }
+    struct stage_regs { uint2 va[4]; uint2 xs; int bc; bool valid; };
     stage_regs st[3];
     auto load_cv = [&](stage_regs& r, int step) {
       const int k = 4 * step + slot;
       r.valid = k < len;
-      r.v0 = make_uint4(0, 0, 0, 0); r.v1 = r.v0; r.xs = make_uint2(0, 0); r.bc = 0;
-      if (r.valid) {
-        const long long blk = (long long)start + k;
-        r.bc = __ldg(block_cols + blk);
-        const uint4* vp = reinterpret_cast<const uint4*>(values + blk * 16);
-        r.v0 = __ldg(vp);
-        r.v1 = __ldg(vp + 1);
+      r.xs = make_uint2(0, 0); r.bc = 0;
+      if (r.valid) r.bc = __ldg(block_cols + (long long)start + k);
+      const int ka = 4 * step + slot_a;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        r.va[j] = make_uint2(0, 0);
+        if (ka < a_len[j])
+          r.va[j] = __ldg(reinterpret_cast<const uint2*>(values + ((long long)a_start[j] + ka) * 16 + row_i * 4));
       }
     };
     auto load_x = [&](stage_regs& r) {
@@ -276,10 +321,11 @@ __global__ void __launch_bounds__(kThreads)
         loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.mma_done[buf]), ((t >> 1) - 1u) & 1u);
       unsigned char* A = sm.a[buf];
       unsigned char* B = sm.b[buf];
-      *reinterpret_cast<uint2*>(A + tile_offset(4 * b + 0, slot)) = make_uint2(r.v0.x, r.v0.y);
-      *reinterpret_cast<uint2*>(A + tile_offset(4 * b + 1, slot)) = make_uint2(r.v0.z, r.v0.w);
-      *reinterpret_cast<uint2*>(A + tile_offset(4 * b + 2, slot)) = make_uint2(r.v1.x, r.v1.y);
-      *reinterpret_cast<uint2*>(A + tile_offset(4 * b + 3, slot)) = make_uint2(r.v1.z, r.v1.w);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ba = 8 * warp + 2 * j + (lane >> 4);       // block-row slot moved by this lane in round j
+        *reinterpret_cast<uint2*>(A + tile_offset(4 * ba + row_i, slot_a)) = r.va[j];
+      }
       *reinterpret_cast<uint2*>(B + tile_offset(b, slot)) = r.xs;
       loops::tma::fence_proxy_async();   // generic-proxy smem writes -> tensor-core (async) proxy
       tc_fence_before_sync();
@@ -326,20 +372,19 @@ __global__ void __launch_bounds__(kThreads)
       if (item.w >= 0) {
         partial[(long long)item.w * 128 + m] = out;   // this chunk's share, reduced in order later
       } else {
-        const int rr_slot = g * kGroupRows + (m >> 2);
-        if (rr_slot < num_block_rows) {
-          const long long row = (long long)__ldg(order + rr_slot) * 4 + (m & 3);
-          if (row < num_rows) y[row] = out;
+        // scalar row m belongs to block-row slot m/4 == b, the slot whose descriptor this thread holds
+        if (row.z >= 0) {
+          const long long yrow = (long long)row.z * 4 + (m & 3);
+          if (yrow < num_rows) y[yrow] = out;
         }
       }
       tc_fence_before_sync();
     } else {
       // every block-row of the group is empty
       const int m = 32 * warp + lane;
-      const int rr_slot = g * kGroupRows + (m >> 2);
-      if (rr_slot < num_block_rows) {
-        const long long row = (long long)__ldg(order + rr_slot) * 4 + (m & 3);
-        if (row < num_rows) y[row] = 0.0f;
+      if (row.z >= 0) {
+        const long long yrow = (long long)row.z * 4 + (m & 3);
+        if (yrow < num_rows) y[yrow] = 0.0f;
       }
     }
     __syncthreads();   // TMEM and both buffers are free for the next group
@@ -377,13 +422,10 @@ inline int run(plan_data* p, const loopsb_layout_t* lay, const uint16_t* values,
                  "values must be 16-byte and x 8-byte aligned");
   if (p->ctas_per_sm == 0) {
     // persistent grid: 8 CTAs per SM measured best on B200 (tools/bcsr_bench.py: 6 -> 137 us,
-    // 8 -> 130 us, 10 -> 147 us, 12 -> 139 us); never more than the registers allow
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_bcsr4x4_bf16_kernel, kThreads, 0) != cudaSuccess ||
-        per_sm < 1)
-      per_sm = 8;
-    (void)cudaGetLastError();
-    per_sm = per_sm < 8 ? per_sm : 8;
+    // 8 -> 130 us, 10 -> 147 us, 12 -> 139 us)
+    // (cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for this kernel on
+    // B200 -- it is not used; 56 registers x 128 threads and 11 KB leave room for 9.)
+    int per_sm = 8;
     if (const char* e = getenv("LOOPSB_BCSR_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
     p->ctas_per_sm = per_sm;
   }
@@ -391,7 +433,7 @@ inline int run(plan_data* p, const loopsb_layout_t* lay, const uint16_t* values,
   if (grid > p->num_items) grid = p->num_items;
   spmv_bcsr4x4_bf16_kernel<<<grid, kThreads, 0, stream>>>(lay->offsets, block_cols, values, x, y, p->order,
                                                         p->num_block_rows, p->items, p->num_items, p->partial,
-                                                        num_rows);
+                                                        num_rows, p->item_rows);
   LOOPSB_CUDA_TRY(cudaGetLastError());
   if (p->num_split > 0) {
     bcsr_split_reduce_kernel<<<p->num_split, 128, 0, stream>>>(p->split, p->partial, p->order, p->num_block_rows,
