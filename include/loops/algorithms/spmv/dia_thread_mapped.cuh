@@ -1,0 +1,4 @@
+/** @file dia_thread_mapped.cuh  algorithms::spmv::dia_thread_mapped is declared in loops/algorithms/spmv/spmv.cuh
+ *  (reference include/loops/algorithms/spmv/dia_thread_mapped.cuh). */
+#pragma once
+#include <loops/algorithms/spmv/spmv.cuh>

@@ -151,6 +151,46 @@ inline util::timer_t ell_merge_path(ell_t<int, float>& ell, vector_t<float>& x, 
                      stream);
 }
 
+/// reference algorithms/spmv/original.cuh:55-72 -- the plain one-thread-per-row kernel; same
+/// arithmetic as thread_mapped (sequential per row), so it is the same sm_100a kernel.
+inline void original(csr_t<int, int, float>& csr, vector_t<float>& x, vector_t<float>& y,
+                     cudaStream_t stream = 0) {
+  thread_mapped(csr, x, y, stream);
+}
+
+/// reference algorithms/spmv/csc_thread_mapped.cuh:54-84 (one thread per column, atomics into y).
+inline util::timer_t csc_thread_mapped(csc_t<int, int, float>& csc, vector_t<float>& x, vector_t<float>& y,
+                                       cudaStream_t stream = 0) {
+  return detail::run(csc.layout().descriptor(), LOOPSB_SCHED_THREAD_MAPPED, detail::raw(csc.values),
+                     detail::raw(csc.indices), nullptr, detail::raw(x), detail::raw(y), csc.rows, csc.cols, stream);
+}
+
+/// reference algorithms/spmv/dia_thread_mapped.cuh:65-98 (one thread per row over the stored diagonals).
+inline util::timer_t dia_thread_mapped(dia_t<int, int, float>& dia, vector_t<float>& x, vector_t<float>& y,
+                                       cudaStream_t stream = 0) {
+  util::timer_t timer(stream);
+  timer.start();
+  error::throw_if_status(
+      loopsb_spmv_dia_f32(static_cast<int32_t>(dia.rows), static_cast<int32_t>(dia.cols),
+                          static_cast<int64_t>(dia.stride), static_cast<int32_t>(dia.num_diagonals),
+                          detail::raw(dia.diag_offsets), detail::raw(dia.values), detail::raw(x), detail::raw(y),
+                          stream),
+      "loopsb_spmv_dia_f32");
+  cudaStreamSynchronize(stream);
+  timer.stop();
+  return timer;
+}
+
+/// reference algorithms/spmv/flat_partitioned.cuh:73-107: thread_mapped over
+/// layout::flat_uniform_occupancy<K, layout::csr> (windows of K nonzeros).
+template <std::size_t K = 8>
+util::timer_t flat_partitioned(csr_t<int, int, float>& csr, vector_t<float>& x, vector_t<float>& y,
+                               cudaStream_t stream = 0) {
+  layout::flat_uniform_occupancy<K, layout::csr<int, int>> lay(csr.layout());
+  return detail::run(lay.descriptor(), LOOPSB_SCHED_THREAD_MAPPED, detail::raw(csr.values),
+                     detail::raw(csr.indices), nullptr, detail::raw(x), detail::raw(y), csr.rows, csr.cols, stream);
+}
+
 template <std::size_t R, std::size_t C>
 util::timer_t bcsr_thread_mapped(bcsr_t<R, C, int, int, float>& bcsr, vector_t<float>& x,
                                  vector_t<float>& y, cudaStream_t stream = 0) {

@@ -231,4 +231,110 @@ struct bcsr_t {
   }
 };
 
+/// CSC: offsets[cols+1], indices[nnzs] = ROW ids, values[nnzs]; entries ordered
+/// by (column, row) (reference container/csc.hxx:88-102).
+template <typename index_t, typename offset_t, typename value_t, memory_space_t space = memory_space_t::device>
+struct csc_t {
+  std::size_t rows = 0, cols = 0, nnzs = 0;
+  vector_t<offset_t, space> offsets;
+  vector_t<index_t, space> indices;
+  vector_t<value_t, space> values;
+
+  csc_t() = default;
+  csc_t(std::size_t r, std::size_t c, std::size_t nnz)
+      : rows(r), cols(c), nnzs(nnz), offsets(c + 1), indices(nnz), values(nnz) {}
+
+  template <auto rhs_space>
+  csc_t(const csc_t<index_t, offset_t, value_t, rhs_space>& rhs)
+      : rows(rhs.rows), cols(rhs.cols), nnzs(rhs.nnzs),
+        offsets(rhs.offsets), indices(rhs.indices), values(rhs.values) {}
+
+  /// From CSR: stable counting sort by column over CSR order.
+  template <auto rhs_space>
+  csc_t(const csr_t<index_t, offset_t, value_t, rhs_space>& csr)
+      : rows(csr.rows), cols(csr.cols), nnzs(csr.nnzs) {
+    thrust::host_vector<offset_t> off(csr.offsets);
+    thrust::host_vector<index_t> idx(csr.indices);
+    thrust::host_vector<value_t> val(csr.values);
+    thrust::host_vector<offset_t> c_off(cols + 1, offset_t(0));
+    for (std::size_t a = 0; a < nnzs; ++a) c_off[idx[a] + 1] += 1;
+    for (std::size_t c = 0; c < cols; ++c) c_off[c + 1] += c_off[c];
+    std::vector<offset_t> cur(c_off.begin(), c_off.end() - 1);
+    thrust::host_vector<index_t> c_row(nnzs);
+    thrust::host_vector<value_t> c_val(nnzs);
+    for (std::size_t r = 0; r < rows; ++r)
+      for (offset_t a = off[r]; a < off[r + 1]; ++a) {
+        const offset_t p = cur[idx[a]]++;
+        c_row[p] = static_cast<index_t>(r);
+        c_val[p] = val[a];
+      }
+    offsets = c_off;
+    indices = c_row;
+    values = c_val;
+  }
+
+  layout::csc<index_t, offset_t> layout() const {
+    return layout::csc<index_t, offset_t>(thrust::raw_pointer_cast(offsets.data()),
+                                          static_cast<index_t>(cols), static_cast<offset_t>(nnzs));
+  }
+};
+
+/// DIA: distinct (col - row) offsets ascending, values column-major
+/// values[d * stride + r], stride = rows (reference container/dia.hxx:56-62,135-188).
+template <typename index_t, typename offset_t, typename value_t, memory_space_t space = memory_space_t::device>
+struct dia_t {
+  std::size_t rows = 0, cols = 0, nnzs = 0, stride = 0, num_diagonals = 0;
+  vector_t<index_t, space> diag_offsets;
+  vector_t<value_t, space> values;
+
+  dia_t() = default;
+
+  template <auto rhs_space>
+  dia_t(const dia_t<index_t, offset_t, value_t, rhs_space>& rhs)
+      : rows(rhs.rows), cols(rhs.cols), nnzs(rhs.nnzs), stride(rhs.stride), num_diagonals(rhs.num_diagonals),
+        diag_offsets(rhs.diag_offsets), values(rhs.values) {}
+
+  template <auto rhs_space, typename csr_offset_t>
+  static std::size_t count_diagonals(const csr_t<index_t, csr_offset_t, value_t, rhs_space>& csr) {
+    return sorted_offsets(csr).size();
+  }
+
+  template <auto rhs_space, typename csr_offset_t>
+  dia_t(const csr_t<index_t, csr_offset_t, value_t, rhs_space>& csr)
+      : rows(csr.rows), cols(csr.cols), nnzs(csr.nnzs), stride(csr.rows) {
+    const std::vector<index_t> offs = sorted_offsets(csr);
+    num_diagonals = offs.size();
+    thrust::host_vector<csr_offset_t> off(csr.offsets);
+    thrust::host_vector<index_t> idx(csr.indices);
+    thrust::host_vector<value_t> val(csr.values);
+    thrust::host_vector<value_t> d_val(num_diagonals * stride, value_t(0));
+    for (std::size_t r = 0; r < rows; ++r)
+      for (csr_offset_t a = off[r]; a < off[r + 1]; ++a) {
+        const index_t o = idx[a] - static_cast<index_t>(r);
+        const std::size_t d = std::lower_bound(offs.begin(), offs.end(), o) - offs.begin();
+        d_val[d * stride + r] = val[a];   // assigned, not added (as the reference)
+      }
+    diag_offsets = thrust::host_vector<index_t>(offs.begin(), offs.end());
+    values = d_val;
+  }
+
+  layout::dia<std::size_t, std::size_t> layout() const {
+    return layout::dia<std::size_t, std::size_t>(rows, num_diagonals);
+  }
+
+ private:
+  template <auto rhs_space, typename csr_offset_t>
+  static std::vector<index_t> sorted_offsets(const csr_t<index_t, csr_offset_t, value_t, rhs_space>& csr) {
+    thrust::host_vector<csr_offset_t> off(csr.offsets);
+    thrust::host_vector<index_t> idx(csr.indices);
+    std::vector<index_t> all;
+    all.reserve(csr.nnzs);
+    for (std::size_t r = 0; r < csr.rows; ++r)
+      for (csr_offset_t a = off[r]; a < off[r + 1]; ++a) all.push_back(idx[a] - static_cast<index_t>(r));
+    std::sort(all.begin(), all.end());
+    all.erase(std::unique(all.begin(), all.end()), all.end());
+    return all;
+  }
+};
+
 }  // namespace loops

@@ -302,7 +302,7 @@ struct flat_uniform_occupancy {
   loopsb_layout_t descriptor() const {
     loopsb_layout_t d{};
     d.kind = LOOPSB_LAYOUT_FLAT;
-    d.offsets = nullptr;
+    d.offsets = base_.descriptor().offsets;   // the base CSR row offsets (tile_of of the base layout)
     d.num_tiles = static_cast<int32_t>(num_tiles());
     d.num_atoms = static_cast<int32_t>(num_atoms());
     d.pitch = static_cast<int32_t>(K);

@@ -144,6 +144,12 @@ int loopsb_plan_probe_collect(loopsb_plan_t* plan, float* host_ms,
  *   algorithms::spmv::coo_thread_mapped coo_thread_mapped.cuh:61-89
  *   algorithms::spmv::ell_thread_mapped ell_thread_mapped.cuh:52-76
  *   algorithms::spmv::ell_merge_path    ell_merge_path.cuh:76-126
+ *   algorithms::spmv::csc_thread_mapped csc_thread_mapped.cuh:54-84   (CSC + thread_mapped:
+ *       tiles are columns, `col_indices` carries the ROW index of every entry)
+ *   algorithms::spmv::flat_partitioned  flat_partitioned.cuh:73-107   (FLAT + thread_mapped:
+ *       descriptor = {kind FLAT, num_tiles = ceil(nnz/K), num_atoms = nnz,
+ *       pitch = K, offsets = the base CSR row offsets})
+ *   algorithms::spmv::original          original.cuh:55-72            (= CSR + thread_mapped)
  * selected by (plan schedule, plan layout kind). `row_indices` is read only
  * for COO. For ELL, `col_indices`/`values` are the row-major rows*pitch slabs
  * with column -1 in padding slots (container/ell.hxx:31-36).
@@ -161,6 +167,14 @@ int loopsb_spmv_bcsr_f32(int32_t R, int32_t C, const loopsb_layout_t* lay,
                          const float* values, const int32_t* block_col_indices,
                          const float* x_padded, float* y, int32_t num_rows,
                          void* stream);
+
+/* DIA: diagonals in ascending offset order, values column-major
+ * values[d * stride + r] (container/dia.hxx:56-62), one thread per row.
+ * Replaces algorithms::spmv::dia_thread_mapped (dia_thread_mapped.cuh:65-98). */
+int loopsb_spmv_dia_f32(int32_t num_rows, int32_t num_cols, int64_t stride,
+                        int32_t num_diagonals, const int32_t* diag_offsets,
+                        const float* values, const float* x, float* y,
+                        void* stream);
 
 /* BCSR 4x4, bf16 values and x, fp32 accumulate and y, on the tcgen05 tensor
  * cores (BASELINE.json config 4). The plan must have been created from a

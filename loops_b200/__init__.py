@@ -7,7 +7,7 @@ streams and ``torch.distributed``. All compute is in ``libloopsb200.so``.
 """
 from . import _lib  # noqa: F401
 from . import layout  # noqa: F401
-from .container import bcsr_t, coo_t, csr_t, ell_t  # noqa: F401
+from .container import bcsr_t, coo_t, csc_t, csr_t, dia_t, ell_t  # noqa: F401
 from . import algorithms  # noqa: F401
 from . import generate  # noqa: F401
 

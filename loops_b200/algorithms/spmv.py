@@ -9,6 +9,10 @@ include/loops/algorithms/spmv/*.cuh), same names and argument meaning:
     ell_thread_mapped(ell, x, y, stream) -> None      ell_thread_mapped.cuh:52-76
     ell_merge_path(ell, x, y, stream)    -> timer_t   ell_merge_path.cuh:76-126
     bcsr_thread_mapped(bcsr, x, y, stream) -> timer_t bcsr_thread_mapped.cuh:88-123
+    csc_thread_mapped(csc, x, y, stream) -> timer_t   csc_thread_mapped.cuh:54-84
+    dia_thread_mapped(dia, x, y, stream) -> timer_t   dia_thread_mapped.cuh:65-98
+    flat_partitioned(csr, x, y, stream, K=8) -> timer_t  flat_partitioned.cuh:73-107
+    original(csr, x, y, stream)          -> None      original.cuh:55-72
 
 Each call goes straight through the C ABI (``loopsb_spmv_f32`` ...) into the
 sm_100a kernels; like the reference wrappers they synchronise the stream before
@@ -22,7 +26,7 @@ from __future__ import annotations
 import torch
 
 from .. import _lib
-from ..container import bcsr_t, coo_t, csr_t, ell_t
+from ..container import bcsr_t, coo_t, csc_t, csr_t, dia_t, ell_t
 
 
 class timer_t:
@@ -108,6 +112,49 @@ def ell_thread_mapped(ell: ell_t, x, y, stream=None, sync=True):
 def ell_merge_path(ell: ell_t, x, y, stream=None, sync=True):
     return _run(ell, _lib.SCHED_MERGE_PATH_FLAT, ell.values, ell.indices, None, x, y, ell.rows,
                 ell.cols, stream, sync, timed=True)
+
+
+def original(csr: csr_t, x, y, stream=None, sync=True):
+    """The plain one-thread-per-row kernel of the reference (original.cuh): the
+    same sequential-per-row arithmetic as thread_mapped, hence the same kernel."""
+    _csr(csr, _lib.SCHED_THREAD_MAPPED, x, y, stream, sync)
+
+
+def csc_thread_mapped(csc: csc_t, x, y, stream=None, sync=True):
+    return _run(csc, _lib.SCHED_THREAD_MAPPED, csc.values, csc.indices, None, x, y, csc.rows, csc.cols,
+                stream, sync, timed=True)
+
+
+def flat_partitioned(csr: csr_t, x, y, stream=None, sync=True, K: int = 8):
+    lib = _lib.load()
+    stream = stream or torch.cuda.current_stream()
+    _check_vec("x", x, csr.cols)
+    _check_vec("y", y, csr.rows)
+    plan = csr.flat_plan(K, stream)
+    timer = timer_t(stream) if sync else None
+    if timer:
+        timer.start()
+    _lib.check(lib.loopsb_spmv_f32(plan.handle, _lib.ptr(csr.values), _lib.ptr(csr.indices), None, _lib.ptr(x),
+                                   _lib.ptr(y), csr.rows, csr.cols, _lib.stream_ptr(stream)), "loopsb_spmv_f32")
+    if timer:
+        timer.stop()
+    return timer
+
+
+def dia_thread_mapped(dia: dia_t, x, y, stream=None, sync=True):
+    lib = _lib.load()
+    stream = stream or torch.cuda.current_stream()
+    _check_vec("x", x, dia.cols)
+    _check_vec("y", y, dia.rows)
+    timer = timer_t(stream) if sync else None
+    if timer:
+        timer.start()
+    _lib.check(lib.loopsb_spmv_dia_f32(dia.rows, dia.cols, dia.stride, dia.num_diagonals,
+                                       _lib.ptr(dia.diag_offsets), _lib.ptr(dia.values), _lib.ptr(x), _lib.ptr(y),
+                                       _lib.stream_ptr(stream)), "loopsb_spmv_dia_f32")
+    if timer:
+        timer.stop()
+    return timer
 
 
 def bcsr_thread_mapped(bcsr: bcsr_t, x, y, stream=None, sync=True):

@@ -14,7 +14,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .layout import csr as csr_layout, coo as coo_layout, ell as ell_layout, bcsr as bcsr_layout
+from .layout import (csr as csr_layout, coo as coo_layout, ell as ell_layout, bcsr as bcsr_layout,
+                     csc as csc_layout, dia as dia_layout, flat_uniform_occupancy)
 
 
 def _dev(a, dtype, device):
@@ -91,6 +92,16 @@ class csr_t(_planned):
     def host(self):
         return (self.offsets.cpu().numpy(), self.indices.cpu().numpy(), self.values.cpu().numpy())
 
+    def flat_plan(self, K: int, stream=None):
+        """thread_mapped plan over layout::flat_uniform_occupancy<K, csr> (cached per K)."""
+        from .plan import Plan
+        key = ("flat", int(K))
+        p = self._plans.get(key)
+        if p is None:
+            p = Plan(flat_uniform_occupancy(K, self.layout()), _lib.SCHED_THREAD_MAPPED, stream)
+            self._plans[key] = p
+        return p
+
 
 class coo_t(_planned):
     """row_indices, col_indices, values, each [nnzs]."""
@@ -141,6 +152,59 @@ class ell_t(_planned):
 
     def layout(self):
         return ell_layout(self.rows, self.pitch)
+
+
+class csc_t(_planned):
+    """offsets[cols+1], indices[nnzs] = ROW ids, values[nnzs]; entries ordered by
+    (column, row) (reference container/csc.hxx:88-102)."""
+
+    def __init__(self, rows, cols, offsets, indices, values, device="cuda"):
+        super().__init__()
+        self.rows, self.cols = int(rows), int(cols)
+        self.offsets = _dev(offsets, torch.int32, device)
+        self.indices = _dev(indices, torch.int32, device)
+        self.values = _dev(values, torch.float32, device)
+        self.nnzs = int(self.indices.numel())
+
+    @classmethod
+    def from_csr(cls, csr: csr_t):
+        off, idx, val = csr.host()
+        r = np.repeat(np.arange(csr.rows, dtype=np.int32), np.diff(off))
+        order = np.argsort(idx, kind="stable")          # (col, row): CSR order is row-major already
+        c_off = np.zeros(csr.cols + 1, dtype=np.int64)
+        np.add.at(c_off, idx.astype(np.int64) + 1, 1)
+        return cls(csr.rows, csr.cols, np.cumsum(c_off).astype(np.int32), r[order], val[order],
+                   device=csr.values.device)
+
+    def layout(self):
+        return csc_layout(self.offsets, self.cols, self.nnzs)
+
+
+class dia_t:
+    """Distinct (col - row) offsets ascending; values column-major
+    values[d * stride + r], stride = rows, entries assigned (reference
+    container/dia.hxx:56-62,135-188)."""
+
+    def __init__(self, rows, cols, nnzs, diag_offsets, values, device="cuda"):
+        self.rows, self.cols, self.nnzs = int(rows), int(cols), int(nnzs)
+        self.stride = self.rows
+        self.diag_offsets = _dev(diag_offsets, torch.int32, device)
+        self.values = _dev(values, torch.float32, device)
+        self.num_diagonals = int(self.diag_offsets.numel())
+
+    @classmethod
+    def from_csr(cls, csr: csr_t):
+        off, idx, val = csr.host()
+        r = np.repeat(np.arange(csr.rows, dtype=np.int64), np.diff(off))
+        o = idx.astype(np.int64) - r
+        offs = np.unique(o)
+        d = np.searchsorted(offs, o)
+        d_val = np.zeros(len(offs) * csr.rows, dtype=np.float32)
+        d_val[d * csr.rows + r] = val                    # assignment, last wins
+        return cls(csr.rows, csr.cols, csr.nnzs, offs.astype(np.int32), d_val, device=csr.values.device)
+
+    def layout(self):
+        return dia_layout(self.rows, self.num_diagonals)
 
 
 class bcsr_t(_planned):

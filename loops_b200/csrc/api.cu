@@ -554,13 +554,20 @@ int loopsb_plan_create(loopsb_plan_t** out, const loopsb_layout_t* lay,
     }
   } else if (schedule == LOOPSB_SCHED_THREAD_MAPPED) {
     if (!(lay->kind == LOOPSB_LAYOUT_CSR || lay->kind == LOOPSB_LAYOUT_COO ||
-          lay->kind == LOOPSB_LAYOUT_ELL || lay->kind == LOOPSB_LAYOUT_BCSR)) {
-      set_error("thread_mapped SpMV exists for CSR, COO, ELL and BCSR here");
+          lay->kind == LOOPSB_LAYOUT_ELL || lay->kind == LOOPSB_LAYOUT_BCSR ||
+          lay->kind == LOOPSB_LAYOUT_CSC || lay->kind == LOOPSB_LAYOUT_FLAT)) {
+      set_error("thread_mapped SpMV exists for CSR, CSC, COO, ELL, BCSR and flat_uniform_occupancy here "
+                "(DIA: loopsb_spmv_dia_f32)");
       return fail(LOOPSB_ERR_UNSUPPORTED);
+    }
+    if (lay->kind == LOOPSB_LAYOUT_FLAT && !(lay->offsets != nullptr && lay->pitch > 0)) {
+      set_error("flat_uniform_occupancy needs the base CSR offsets and K > 0");
+      return fail(LOOPSB_ERR_INVALID);
     }
     p->cta_threads = 128;
     p->grid = (T + 127) / 128;
-    p->launches = lay->kind == LOOPSB_LAYOUT_COO ? 2 : 1;
+    p->launches = (lay->kind == LOOPSB_LAYOUT_COO || lay->kind == LOOPSB_LAYOUT_CSC ||
+                   lay->kind == LOOPSB_LAYOUT_FLAT) ? 2 : 1;
     if (lay->kind == LOOPSB_LAYOUT_BCSR) {
       int rc = bcsr_tc::create(&p->tc, lay, dp->sm_count, s);
       if (rc != LOOPSB_OK) return fail(rc);
@@ -761,6 +768,8 @@ int loopsb_spmv_f32(loopsb_plan_t* plan, const float* values,
         LOOPSB_REQUIRE(row_indices != nullptr, "COO needs row_indices");
         LOOPSB_CUDA_TRY(cudaMemsetAsync(y, 0, size_t(num_rows) * sizeof(float), s));
       }
+      if (lay.kind == LOOPSB_LAYOUT_CSC || lay.kind == LOOPSB_LAYOUT_FLAT)   // scatter kernels accumulate into y
+        LOOPSB_CUDA_TRY(cudaMemsetAsync(y, 0, size_t(num_rows) * sizeof(float), s));
       probe_scope probe(plan, s);
       if (lay.kind == LOOPSB_LAYOUT_CSR) {
         LOOPSB_REQUIRE(T == num_rows, "layout tiles must equal num_rows");
@@ -773,6 +782,14 @@ int loopsb_spmv_f32(loopsb_plan_t* plan, const float* values,
         LOOPSB_REQUIRE(T == num_rows, "layout tiles must equal num_rows");
         sk::spmv_ell_thread_mapped<<<plan->grid, 128, 0, s>>>(
             col_indices, values, x, y, num_rows, lay.pitch);
+      } else if (lay.kind == LOOPSB_LAYOUT_CSC) {
+        // tiles are columns; `col_indices` carries the ROW index of every stored entry
+        LOOPSB_REQUIRE(T == num_cols, "CSC layout tiles must equal num_cols");
+        sk::spmv_csc_thread_mapped<<<plan->grid, 128, 0, s>>>(lay.offsets, col_indices, values, x, y, num_cols);
+      } else if (lay.kind == LOOPSB_LAYOUT_FLAT) {
+        // tiles are windows of K = pitch atoms over the base CSR whose offsets the descriptor carries
+        sk::spmv_flat_partitioned<<<plan->grid, 128, 0, s>>>(lay.offsets, col_indices, values, x, y, num_rows, A,
+                                                             lay.pitch);
       } else {
         set_error("use loopsb_spmv_bcsr_f32 / loopsb_spmv_bcsr4x4_bf16 for BCSR");
         return LOOPSB_ERR_UNSUPPORTED;
@@ -835,6 +852,22 @@ int loopsb_spmv_bcsr_f32(int32_t R, int32_t C, const loopsb_layout_t* lay,
     set_error("BCSR block shape %dx%d not instantiated (2x2, 3x3, 4x4)", R, C);
     return LOOPSB_ERR_UNSUPPORTED;
   }
+  LOOPSB_CUDA_TRY(cudaGetLastError());
+  return LOOPSB_OK;
+}
+
+int loopsb_spmv_dia_f32(int32_t num_rows, int32_t num_cols, int64_t stride, int32_t num_diagonals,
+                        const int32_t* diag_offsets, const float* values, const float* x, float* y,
+                        void* stream) {
+  LOOPSB_REQUIRE(num_rows >= 0 && num_cols >= 0 && num_diagonals >= 0 && stride >= num_rows,
+                 "negative size or stride shorter than the rows");
+  if (current_device() == nullptr) return LOOPSB_ERR_CUDA;
+  if (num_rows == 0) return LOOPSB_OK;
+  LOOPSB_REQUIRE(y != nullptr, "y is null");
+  LOOPSB_REQUIRE(num_diagonals == 0 || (diag_offsets && values && x), "null matrix / x pointer");
+  cudaStream_t s = as_stream(stream);
+  sk::spmv_dia_thread_mapped<<<(num_rows + 127) / 128, 128, 0, s>>>(diag_offsets, values, x, y, num_rows, num_cols,
+                                                                   stride, num_diagonals);
   LOOPSB_CUDA_TRY(cudaGetLastError());
   return LOOPSB_OK;
 }

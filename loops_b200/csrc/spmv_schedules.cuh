@@ -302,6 +302,87 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// --------------------------------------------------------------------- csc --
+// Replaces reference algorithms/spmv/csc_thread_mapped.cuh:29-41: one thread
+// per column (tile), x[col] read once, one atomic per stored entry (the format
+// scatters rows, there is nothing to reduce locally). y is zeroed by the caller
+// side of the C ABI.
+__global__ void __launch_bounds__(128)
+    spmv_csc_thread_mapped(const int* __restrict__ offsets,
+                           const int* __restrict__ row_indices,
+                           const float* __restrict__ values,
+                           const float* __restrict__ x, float* __restrict__ y,
+                           int cols) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < cols; col += stride) {
+    const float xc = __ldg(x + col);
+    const int end = __ldg(offsets + col + 1);
+    for (int a = __ldg(offsets + col); a < end; ++a)
+      atomicAdd(y + __ldg(row_indices + a), __fmul_rn(__ldg(values + a), xc));
+  }
+}
+
+// --------------------------------------------------------------------- dia --
+// Replaces reference algorithms/spmv/dia_thread_mapped.cuh:33-54: one thread
+// per row, diagonals in ascending offset order (= ascending column), values
+// column-major values[d * stride + r] so a warp reads 128 contiguous bytes per
+// diagonal. Un-fused multiply/add: bit-identical to the CPU validator.
+__global__ void __launch_bounds__(128)
+    spmv_dia_thread_mapped(const int* __restrict__ diag_offsets,
+                           const float* __restrict__ values,
+                           const float* __restrict__ x, float* __restrict__ y,
+                           int rows, int cols, long long stride_elems, int num_diagonals) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += stride) {
+    float acc = 0.0f;
+    for (int d = 0; d < num_diagonals; ++d) {
+      const long long c = (long long)r + __ldg(diag_offsets + d);
+      if (c >= 0 && c < cols)
+        acc = __fadd_rn(acc, __fmul_rn(__ldg(values + (long long)d * stride_elems + r), __ldg(x + c)));
+    }
+    y[r] = acc;
+  }
+}
+
+// ----------------------------------------------------- flat_uniform_occupancy --
+// Replaces reference algorithms/spmv/flat_partitioned.cuh:46-60: one thread per
+// window of K consecutive atoms (layout::flat_uniform_occupancy<K, csr>). The
+// reference finds the row of EVERY atom with an upper_bound search and issues
+// one atomic per atom; here the search runs once per window, the rows are then
+// walked, and one atomic goes out per (window, row) run.
+__global__ void __launch_bounds__(128)
+    spmv_flat_partitioned(const int* __restrict__ offsets,
+                          const int* __restrict__ indices,
+                          const float* __restrict__ values,
+                          const float* __restrict__ x, float* __restrict__ y,
+                          int rows, int nnz, int K) {
+  const long long windows = ((long long)nnz + K - 1) / K;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < windows; t += stride) {
+    const int a0 = int(t * K);
+    const int a1 = min(nnz, a0 + K);
+    // row of atom a0: last row whose begin offset is <= a0 (base.tile_of)
+    int lo = 0, hi = rows;   // invariant: offsets[lo] <= a0 < offsets[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(offsets + mid) <= a0) lo = mid; else hi = mid;
+    }
+    int row = lo;
+    int row_end = __ldg(offsets + row + 1);
+    float acc = 0.0f;
+    for (int a = a0; a < a1; ++a) {
+      while (a >= row_end) {            // close the run (empty rows are skipped)
+        if (acc != 0.0f) atomicAdd(y + row, acc);
+        acc = 0.0f;
+        ++row;
+        row_end = __ldg(offsets + row + 1);
+      }
+      acc = __fadd_rn(acc, __fmul_rn(__ldg(values + a), __ldg(x + __ldg(indices + a))));
+    }
+    if (acc != 0.0f) atomicAdd(y + row, acc);
+  }
+}
+
 // -------------------------------------------------------------------- bcsr --
 template <int R, int C>
 __global__ void __launch_bounds__(128)

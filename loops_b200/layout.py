@@ -74,3 +74,22 @@ class ell(_pitch_view):
 
 class dia(_pitch_view):
     kind = _lib.LAYOUT_DIA
+
+
+class flat_uniform_occupancy(_view):
+    """Windows of K consecutive atoms over a base offsets layout (reference
+    container/partitioning.hxx:71-141): tile_end(t) = min((t+1)K, A); the base
+    layout (``base()``) keeps answering tile_of."""
+    kind = _lib.LAYOUT_FLAT
+
+    def __init__(self, K: int, base: _offsets_view):
+        assert K > 0
+        self.pitch, self._base = int(K), base
+        self.offsets = base.offsets
+
+    def base(self): return self._base
+    def num_atoms(self): return self._base.num_atoms()
+    def num_tiles(self): return (self.num_atoms() + self.pitch - 1) // self.pitch
+    def tile_begin(self, t): return t * self.pitch
+    def tile_end(self, t): return min((t + 1) * self.pitch, self.num_atoms())
+    def tile_size(self, t): return self.tile_end(t) - self.tile_begin(t)

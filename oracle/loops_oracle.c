@@ -515,3 +515,85 @@ float orc_bf16_round(float f) {
   memcpy(&f, &u, 4);
   return f;
 }
+
+/* ---- CSC / DIA / flat_uniform_occupancy ----------------------
+ * csc_t(csr_t): container/csc.hxx:88-102 -- the CSR entries re-sorted by
+ * (column, row) (coo.hxx:116-122 sorts the zipped (col, row) keys) and the
+ * column ids compressed into offsets (detail/convert.hxx:70-78). A stable
+ * counting sort over CSR order gives exactly that order when (row, col) pairs
+ * are unique. */
+void orc_csr_to_csc(i32 rows, i32 cols, const i32* off, const i32* idx, const float* val,
+                    i32* c_off /* cols+1 */, i32* c_row /* nnz */, float* c_val /* nnz */) {
+  for (i32 c = 0; c <= cols; ++c) c_off[c] = 0;
+  for (i64 a = 0; a < off[rows]; ++a) c_off[idx[a] + 1] += 1;
+  for (i32 c = 0; c < cols; ++c) c_off[c + 1] += c_off[c];
+  i32* cur = (i32*)malloc(sizeof(i32) * (size_t)(cols > 0 ? cols : 1));
+  for (i32 c = 0; c < cols; ++c) cur[c] = c_off[c];
+  for (i32 r = 0; r < rows; ++r)
+    for (i32 a = off[r]; a < off[r + 1]; ++a) {
+      i32 p = cur[idx[a]]++;
+      c_row[p] = r;
+      c_val[p] = val[a];
+    }
+  free(cur);
+}
+/* algorithms/spmv/csc_thread_mapped.cuh:29-41 (sequential restatement: columns
+ * ascending, entries of a column in stored order; y pre-zeroed). */
+void orc_spmv_csc(i32 cols, const i32* c_off, const i32* c_row, const float* c_val,
+                  const float* x, float* y /* pre-zeroed, rows */) {
+  for (i32 c = 0; c < cols; ++c)
+    for (i32 a = c_off[c]; a < c_off[c + 1]; ++a) {
+      volatile float p = c_val[a] * x[c];
+      y[c_row[a]] = y[c_row[a]] + p;
+    }
+}
+/* dia_t(csr_t): container/dia.hxx:135-188 -- distinct (col - row) offsets in
+ * ascending order, stride = rows, values[d*stride + r] assigned (not added). */
+i32 orc_dia_offsets(i32 rows, const i32* off, const i32* idx, i32* out /* cap >= nnz, or NULL to count */,
+                    i32 cap) {
+  i64 nnz = off[rows];
+  i32* all = (i32*)malloc(sizeof(i32) * (size_t)(nnz > 0 ? nnz : 1));
+  for (i32 r = 0; r < rows; ++r)
+    for (i32 a = off[r]; a < off[r + 1]; ++a) all[a] = idx[a] - r;
+  qsort(all, (size_t)nnz, sizeof(i32), cmp_i32);
+  i32 n = 0;
+  for (i64 a = 0; a < nnz; ++a)
+    if (a == 0 || all[a] != all[a - 1]) { if (out && n < cap) out[n] = all[a]; ++n; }
+  free(all);
+  return n;
+}
+void orc_csr_to_dia(i32 rows, const i32* off, const i32* idx, const float* val, i32 num_diagonals,
+                    const i32* diag_offsets, float* d_val /* num_diagonals * rows, pre-zeroed */) {
+  for (i32 r = 0; r < rows; ++r)
+    for (i32 a = off[r]; a < off[r + 1]; ++a) {
+      i32 o = idx[a] - r, lo = 0, hi = num_diagonals;   /* lower_bound over the sorted offsets */
+      while (lo < hi) { i32 mid = (lo + hi) / 2; if (diag_offsets[mid] < o) lo = mid + 1; else hi = mid; }
+      d_val[(i64)lo * rows + r] = val[a];
+    }
+}
+/* algorithms/spmv/dia_thread_mapped.cuh:33-54: per row, diagonals ascending. */
+void orc_spmv_dia(i32 rows, i32 cols, i64 stride, i32 num_diagonals, const i32* diag_offsets,
+                  const float* d_val, const float* x, float* y) {
+  for (i32 r = 0; r < rows; ++r) {
+    volatile float acc = 0.0f;
+    for (i32 d = 0; d < num_diagonals; ++d) {
+      i64 c = (i64)r + diag_offsets[d];
+      if (c >= 0 && c < cols) { volatile float p = d_val[(i64)d * stride + r] * x[c]; acc = acc + p; }
+    }
+    y[r] = acc;
+  }
+}
+/* algorithms/spmv/flat_partitioned.cuh:46-60 over layout::flat_uniform_occupancy<K, csr>
+ * (container/partitioning.hxx:71-141): windows of K atoms, row = base.tile_of(atom)
+ * (layout.hxx:137-148), one add per atom in window order; y pre-zeroed. */
+void orc_spmv_flat_partitioned(i32 rows, i32 K, const i32* off, const i32* idx, const float* val,
+                               const float* x, float* y /* pre-zeroed */) {
+  i64 nnz = off[rows];
+  for (i64 t = 0; t * K < nnz; ++t)
+    for (i64 a = t * K; a < (t + 1) * K && a < nnz; ++a) {
+      i32 lo = 0, hi = rows;                       /* upper_bound(offsets, a) - 1 */
+      while (hi - lo > 1) { i32 mid = (lo + hi) / 2; if (off[mid] <= a) lo = mid; else hi = mid; }
+      volatile float p = val[a] * x[idx[a]];
+      y[lo] = y[lo] + p;
+    }
+}

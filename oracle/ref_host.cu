@@ -19,6 +19,8 @@
 //   include/loops/container/ell.hxx:113-145    ell_t(csr_t)
 //   include/loops/container/bcsr.hxx:111-194   bcsr_t(csr_t)
 //   include/loops/container/coo.hxx:87-98      coo_t(csr_t)
+//   include/loops/container/csc.hxx:88-102     csc_t(csr_t)
+//   include/loops/container/dia.hxx:135-188    dia_t(csr_t)
 
 #include <loops/container/formats.hxx>
 #include <loops/container/market.hxx>
@@ -175,6 +177,30 @@ int ref_csr_to_bcsr(int R, int rows, int cols, int nnz, const int* off,
     default:
       return 1;
   }
+}
+
+// csc_t(csr_t): column offsets, row indices and values in the container's order.
+void ref_csr_to_csc(int rows, int cols, int nnz, const int* off, const int* idx,
+                    const float* val, int* c_off, int* c_row, float* c_val) {
+  csr_h c = make_csr(rows, cols, nnz, off, idx, val);
+  csc_t<int, int, float, memory_space_t::host> s(c);
+  std::copy(s.offsets.begin(), s.offsets.end(), c_off);
+  std::copy(s.indices.begin(), s.indices.end(), c_row);
+  std::copy(s.values.begin(), s.values.end(), c_val);
+}
+
+// dia_t(csr_t): returns num_diagonals; fills the arrays when they are non-null
+// and large enough (diag_offsets[num_diagonals], values[num_diagonals * rows]).
+int ref_csr_to_dia(int rows, int cols, int nnz, const int* off, const int* idx,
+                   const float* val, int* diag_offsets, float* d_val, int cap_diagonals) {
+  csr_h c = make_csr(rows, cols, nnz, off, idx, val);
+  dia_t<int, int, float, memory_space_t::host> d(c);
+  const int n = (int)d.num_diagonals;
+  if (diag_offsets && d_val && n <= cap_diagonals) {
+    std::copy(d.diag_offsets.begin(), d.diag_offsets.end(), diag_offsets);
+    std::copy(d.values.begin(), d.values.end(), d_val);
+  }
+  return n;
 }
 
 // ---- CPU baseline timing ---------------------------------------------------

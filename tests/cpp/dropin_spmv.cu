@@ -135,6 +135,44 @@ int main() {
     }
     if (!plan.band_tiled()) { std::printf("FAIL merge_path_plan_t did not tile\n"); ++failures; }
     check("algorithms::spmv::merge_path_plan_t (band-tiled)", y, ref);
+    // the remaining in-tree entry points: original, csc, dia (on a banded matrix), flat_partitioned
+    thrust::fill(y.begin(), y.end(), -1.0f);
+    algorithms::spmv::original(csr, x, y);
+    check("algorithms::spmv::original", y, ref);
+    csc_t<int, int, float> csc(csr);
+    thrust::fill(y.begin(), y.end(), -1.0f);
+    algorithms::spmv::csc_thread_mapped(csc, x, y);
+    check("algorithms::spmv::csc_thread_mapped", y, ref);
+    thrust::fill(y.begin(), y.end(), -1.0f);
+    algorithms::spmv::flat_partitioned<8>(csr, x, y);
+    check("algorithms::spmv::flat_partitioned<8>", y, ref);
+    {
+      const int n = 600;
+      csr_host_t hb(n, n, 0);
+      std::vector<int> boff(n + 1, 0), bidx;
+      std::vector<float> bval;
+      for (int r = 0; r < n; ++r) {
+        for (int d : {-7, -1, 0, 2, 31})
+          if (r + d >= 0 && r + d < n && (r + d) % 5 != 0) { bidx.push_back(r + d); bval.push_back(val(rng)); }
+        boff[r + 1] = int(bidx.size());
+      }
+      csr_host_t hb2(n, n, bidx.size());
+      std::copy(boff.begin(), boff.end(), hb2.offsets.begin());
+      std::copy(bidx.begin(), bidx.end(), hb2.indices.begin());
+      std::copy(bval.begin(), bval.end(), hb2.values.begin());
+      std::vector<float> bref(n, 0.0f);
+      for (int r = 0; r < n; ++r) {
+        float sum = 0;
+        for (int k = boff[r]; k < boff[r + 1]; ++k) sum += bval[k] * xs[bidx[k]];
+        bref[r] = sum;
+      }
+      csr_t<int, int, float> band(hb2);
+      dia_t<int, int, float> dia(band);
+      vector_t<float> yb(n);
+      thrust::fill(yb.begin(), yb.end(), -1.0f);
+      algorithms::spmv::dia_thread_mapped(dia, x, yb);
+      check("algorithms::spmv::dia_thread_mapped", yb, bref);
+    }
     std::printf("   timer_t: %.3f ms\n", t.milliseconds());
     algorithms::spmv::work_oriented(csr, x, y);   check("algorithms::spmv::work_oriented", y, ref);
     algorithms::spmv::thread_mapped(csr, x, y);   check("algorithms::spmv::thread_mapped", y, ref);

@@ -158,6 +158,41 @@ class Oracle:
         self.L.orc_csr_to_bcsr(R, Cc, rows, cols, P(off), P(idx), P(val), C.byref(nb), P(b_off), P(b_col), P(b_val))
         return b_off, b_col, b_val
 
+    def csc(self, rows, cols, off, idx, val):
+        nnz = int(off[-1])
+        c_off = np.zeros(cols + 1, np.int32)
+        c_row = np.zeros(nnz, np.int32)
+        c_val = np.zeros(nnz, np.float32)
+        self.L.orc_csr_to_csc(rows, cols, P(off), P(idx), P(val), P(c_off), P(c_row), P(c_val))
+        return c_off, c_row, c_val
+
+    def spmv_csc(self, rows, c_off, c_row, c_val, x):
+        y = np.zeros(rows, np.float32)
+        self.L.orc_spmv_csc(len(c_off) - 1, P(c_off), P(c_row), P(c_val), P(x), P(y))
+        return y
+
+    def dia(self, rows, off, idx, val):
+        """(diag_offsets i32[nd], values f32[nd * rows]) -- stride == rows."""
+        nd = self.L.orc_dia_offsets(rows, P(off), P(idx), None, 0)
+        d_off = np.zeros(max(nd, 1), np.int32)[:nd].copy() if nd else np.zeros(0, np.int32)
+        if nd:
+            self.L.orc_dia_offsets(rows, P(off), P(idx), P(d_off), nd)
+        d_val = np.zeros(nd * rows, np.float32)
+        if nd:
+            self.L.orc_csr_to_dia(rows, P(off), P(idx), P(val), nd, P(d_off), P(d_val))
+        return d_off, d_val
+
+    def spmv_dia(self, rows, cols, d_off, d_val, x):
+        y = np.zeros(rows, np.float32)
+        self.L.orc_spmv_dia(rows, cols, C.c_int64(rows), len(d_off), P(d_off), P(d_val), P(x), P(y))
+        return y
+
+    def spmv_flat_partitioned(self, K, off, idx, val, x):
+        rows = len(off) - 1
+        y = np.zeros(rows, np.float32)
+        self.L.orc_spmv_flat_partitioned(rows, K, P(off), P(idx), P(val), P(x), P(y))
+        return y
+
     def spmv_coo(self, rows, row, col, val, x):
         y = np.zeros(rows, np.float32)
         self.L.orc_spmv_coo(C.c_int64(len(val)), P(row), P(col), P(val), P(x), P(y))

@@ -82,6 +82,80 @@ def test_battery_coo_ell(oracle, battery):
         np.testing.assert_array_equal(y.cpu().numpy(), b["y"])      # sequential -> exact
 
 
+def test_battery_csc_dia_flat_original(oracle, battery):
+    """The remaining in-tree entry points (unittests/test_spmv_csc.cu, test_spmv_dia.cu,
+    test_spmv_partitioned.cu; algorithms/spmv/original.cuh): containers equal the
+    oracle's conversions (pinned to the reference headers on CPU), y within the
+    north_star tolerance; the sequential kernels (dia, original) bit-exact."""
+    from loops_b200 import csc_t, csr_t, dia_t
+    from loops_b200.algorithms import spmv
+    for b in battery:
+        rows, cols = b["rows"], b["cols"]
+        A = csr_t(rows, cols, b["off"], b["idx"], b["val"])
+        x = torch.as_tensor(b["x"]).cuda()
+        label = lambda n: (n, b["name"])
+        csc = csc_t.from_csr(A)
+        c_off, c_row, c_val = oracle.csc(rows, cols, b["off"], b["idx"], b["val"])
+        np.testing.assert_array_equal(csc.offsets.cpu().numpy(), c_off)
+        np.testing.assert_array_equal(csc.indices.cpu().numpy(), c_row)
+        np.testing.assert_array_equal(csc.values.cpu().numpy(), c_val)
+        y = torch.full((rows,), float("nan"), device="cuda")
+        spmv.csc_thread_mapped(csc, x, y)
+        _assert_close(oracle, b["off"], b["idx"], b["val"], b["x"], y.cpu().numpy(), label("csc_thread_mapped"))
+        for K in (1, 8, 13):
+            y = torch.full((rows,), float("nan"), device="cuda")
+            spmv.flat_partitioned(A, x, y, K=K)
+            _assert_close(oracle, b["off"], b["idx"], b["val"], b["x"], y.cpu().numpy(), label(f"flat_partitioned<{K}>"))
+        y = torch.full((rows,), float("nan"), device="cuda")
+        spmv.original(A, x, y)
+        np.testing.assert_array_equal(y.cpu().numpy(), b["y"])
+        d_off, d_val = oracle.dia(rows, b["off"], b["idx"], b["val"])
+        if len(d_off) * rows <= (1 << 24):          # DIA of a scattered matrix is huge; keep it sane
+            dia = dia_t.from_csr(A)
+            np.testing.assert_array_equal(dia.diag_offsets.cpu().numpy(), d_off)
+            np.testing.assert_array_equal(dia.values.cpu().numpy(), d_val)
+            y = torch.full((rows,), float("nan"), device="cuda")
+            spmv.dia_thread_mapped(dia, x, y)
+            np.testing.assert_array_equal(y.cpu().numpy(), oracle.spmv_dia(rows, cols, d_off, d_val, b["x"]))
+            np.testing.assert_array_equal(y.cpu().numpy(), b["y"])      # ascending diagonals == ascending columns
+
+
+def test_csc_flat_exact_inputs_and_banded_dia(oracle):
+    from loops_b200 import csc_t, csr_t, dia_t
+    from loops_b200.algorithms import spmv
+    off, idx, val = random_csr(3000, 2500, 0.004, seed=21, empty_every=9, heavy_row=(5, 2000), exact=True)
+    x = oracle.x_recipe_int(2500)
+    want = oracle.spmv(off, idx, val, x)
+    A = csr_t(3000, 2500, off, idx, val)
+    xd = torch.as_tensor(x).cuda()
+    for fn, M, kw in ((spmv.csc_thread_mapped, csc_t.from_csr(A), {}), (spmv.flat_partitioned, A, {"K": 8}),
+                      (spmv.flat_partitioned, A, {"K": 128}), (spmv.original, A, {})):
+        y = torch.full((3000,), float("nan"), device="cuda")
+        fn(M, xd, y, **kw)
+        np.testing.assert_array_equal(y.cpu().numpy(), want, err_msg=fn.__name__)
+    # a banded matrix (7 diagonals, some entries missing) in DIA, general floats
+    n = 5000
+    rng = np.random.default_rng(4)
+    rows_l, cols_l = [], []
+    for d in (-40, -3, -1, 0, 1, 2, 57):
+        r = np.arange(max(0, -d), min(n, n - d))
+        keep = rng.random(len(r)) < 0.9
+        rows_l.append(r[keep]); cols_l.append(r[keep] + d)
+    r, c = np.concatenate(rows_l), np.concatenate(cols_l)
+    order = np.lexsort((c, r))
+    r, c = r[order], c[order]
+    off = np.zeros(n + 1, np.int32); np.add.at(off, r + 1, 1); off = np.cumsum(off).astype(np.int32)
+    idx = c.astype(np.int32)
+    val = rng.uniform(0.5, 1.5, len(idx)).astype(np.float32)
+    x = rng.uniform(-1, 1, n).astype(np.float32)
+    A = csr_t(n, n, off, idx, val)
+    dia = dia_t.from_csr(A)
+    assert dia.num_diagonals == 7
+    y = torch.full((n,), float("nan"), device="cuda")
+    spmv.dia_thread_mapped(dia, torch.as_tensor(x).cuda(), y)
+    np.testing.assert_array_equal(y.cpu().numpy(), oracle.spmv(off, idx, val, x))   # same order, un-fused
+
+
 @pytest.mark.parametrize("R", [2, 3, 4])
 def test_battery_bcsr_f32(oracle, battery, R):
     """unittests/test_spmv_bcsr.cu:24-42 (2x2, 3x3) + 4x4, padded x."""

@@ -149,3 +149,25 @@ def test_powerlaw_2_16_rows_default_geometry(oracle):
     y, info = _run(off, idx, val, x, rows, cols, None, repeat=3, want_info=True)
     np.testing.assert_array_equal(y, oracle.spmv(off, idx, val, x))
     assert info["real_entries"] == rows * 32
+
+
+def test_full_size_config2_tiled_equals_plain():
+    """BASELINE config 2 at full size: the band-tiled kernel (what bench.py times)
+    and the plain CSR merge-path kernel give the same bits on the exact workload,
+    launch after launch; the cost model accepts the matrix without being forced."""
+    from loops_b200 import _lib, csr_t, generate as g
+    from loops_b200.algorithms import spmv
+    rows = cols = 1 << 20
+    off, idx, val = g.synth_csr(rows, cols, 1 << 25, device="cuda")
+    x = g.x_recipe(cols, device="cuda")
+    A = csr_t.from_tensors(rows, cols, off, idx, val)
+    y_plain = torch.full((rows,), float("nan"), device="cuda")
+    spmv.merge_path_flat(A, x, y_plain, tiled=False)
+    assert A.plan(_lib.SCHED_MERGE_PATH_FLAT, tiled=False).tiled_info() is None
+    y = torch.full((rows,), float("nan"), device="cuda")
+    for _ in range(3):
+        y.fill_(float("nan"))
+        spmv.merge_path_flat(A, x, y, tiled="auto")
+        assert torch.equal(y, y_plain)
+    info = A.plan(_lib.SCHED_MERGE_PATH_FLAT, tiled="auto").tiled_info()
+    assert info is not None and info["flagged_steps"] * 20 <= info["total_steps"]

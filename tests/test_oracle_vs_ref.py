@@ -47,6 +47,34 @@ def test_conversions(oracle, ref_host, rows, cols, dens, seed, empty, heavy):
         np.testing.assert_array_equal(b_val, g_val)
 
 
+@pytest.mark.parametrize("rows,cols,dens,seed,empty,heavy", CASES)
+def test_csc_dia_conversions_and_their_spmv(oracle, ref_host, rows, cols, dens, seed, empty, heavy):
+    """csc_t(csr) / dia_t(csr) (container/csc.hxx:88-102, dia.hxx:135-188) and the
+    sequential restatements of the csc / dia / flat_partitioned SpMV kernels: on
+    exact inputs every order of the adds gives the validator's y."""
+    off, idx, val = random_csr(rows, cols, dens, seed, empty, heavy, exact=True)
+    nnz = len(idx)
+    c_off, c_row, c_val = oracle.csc(rows, cols, off, idx, val)
+    g_off, g_row, g_val = np.zeros_like(c_off), np.zeros_like(c_row), np.zeros_like(c_val)
+    ref_host.ref_csr_to_csc(rows, cols, nnz, P(off), P(idx), P(val), P(g_off), P(g_row), P(g_val))
+    np.testing.assert_array_equal(c_off, g_off)
+    np.testing.assert_array_equal(c_row, g_row)
+    np.testing.assert_array_equal(c_val, g_val)
+    d_off, d_val = oracle.dia(rows, off, idx, val)
+    nd = ref_host.ref_csr_to_dia(rows, cols, nnz, P(off), P(idx), P(val), None, None, 0)
+    assert nd == len(d_off)
+    r_off, r_val = np.zeros_like(d_off), np.zeros_like(d_val)
+    assert ref_host.ref_csr_to_dia(rows, cols, nnz, P(off), P(idx), P(val), P(r_off), P(r_val), nd) == nd
+    np.testing.assert_array_equal(d_off, r_off)
+    np.testing.assert_array_equal(d_val, r_val)
+    x = oracle.x_recipe_int(cols)
+    want = oracle.spmv(off, idx, val, x)
+    np.testing.assert_array_equal(oracle.spmv_csc(rows, c_off, c_row, c_val, x), want)
+    np.testing.assert_array_equal(oracle.spmv_dia(rows, cols, d_off, d_val, x), want)
+    for K in (1, 8, 13):
+        np.testing.assert_array_equal(oracle.spmv_flat_partitioned(K, off, idx, val, x), want)
+
+
 def test_x_recipe(oracle, ref_host):
     for seed in (42, 1, 123456789):
         for (lo, hi) in ((1, 10), (0, 1), (-5, 5)):
