@@ -176,6 +176,13 @@ int loopsb_spmv_dia_f32(int32_t num_rows, int32_t num_cols, int64_t stride,
                         const float* values, const float* x, float* y,
                         void* stream);
 
+/* SpMM  C = A * B, A in CSR (fp32), B [num_cols x n] and C [num_rows x n] dense
+ * row-major. Replaces algorithms::spmm::thread_mapped (spmm/thread_mapped.cuh:55-80)
+ * over container/matrix.cuh. C is fully overwritten. */
+int loopsb_spmm_csr_f32(const loopsb_layout_t* lay, const float* values,
+                        const int32_t* col_indices, const float* B, float* C,
+                        int32_t num_rows, int32_t num_cols, int32_t n, void* stream);
+
 /* BCSR 4x4, bf16 values and x, fp32 accumulate and y, on the tcgen05 tensor
  * cores (BASELINE.json config 4). The plan must have been created from a
  * LOOPSB_LAYOUT_BCSR descriptor with LOOPSB_SCHED_THREAD_MAPPED. */

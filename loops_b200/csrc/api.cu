@@ -872,6 +872,22 @@ int loopsb_spmv_dia_f32(int32_t num_rows, int32_t num_cols, int64_t stride, int3
   return LOOPSB_OK;
 }
 
+int loopsb_spmm_csr_f32(const loopsb_layout_t* lay, const float* values, const int32_t* col_indices,
+                        const float* B, float* C, int32_t num_rows, int32_t num_cols, int32_t n,
+                        void* stream) {
+  LOOPSB_REQUIRE(lay != nullptr && lay->kind == LOOPSB_LAYOUT_CSR && lay->offsets != nullptr, "CSR layout required");
+  LOOPSB_REQUIRE(num_rows >= 0 && num_cols >= 0 && n >= 0 && lay->num_tiles == num_rows, "bad dimensions");
+  if (current_device() == nullptr) return LOOPSB_ERR_CUDA;
+  if (num_rows == 0 || n == 0) return LOOPSB_OK;
+  LOOPSB_REQUIRE(C != nullptr, "C is null");
+  LOOPSB_REQUIRE(lay->num_atoms == 0 || (values && col_indices && B), "null matrix / B pointer");
+  const dim3 grid((num_rows + 3) / 4, (n + 31) / 32);
+  LOOPSB_REQUIRE(grid.y <= 65535u, "more than 2M dense columns");
+  sk::spmm_csr_row_warp<<<grid, 128, 0, as_stream(stream)>>>(lay->offsets, col_indices, values, B, C, num_rows, n);
+  LOOPSB_CUDA_TRY(cudaGetLastError());
+  return LOOPSB_OK;
+}
+
 int loopsb_spmv_bcsr4x4_bf16(loopsb_plan_t* plan, const uint16_t* values_bf16,
                              const int32_t* block_col_indices,
                              const uint16_t* x_bf16_padded, float* y,

@@ -383,6 +383,39 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// -------------------------------------------------------------------- spmm --
+// C[row, :] = sum_nz values[nz] * B[indices[nz], :]   (B, C row-major, n columns)
+// Replaces reference algorithms/spmm/thread_mapped.cuh:28-53, whose one thread per
+// row walks B column by column (stride-n reads). Here a warp owns one row and a
+// slab of 32 columns: every stored entry costs one broadcast (value, index) load
+// and ONE coalesced 128-byte read of B. Per (row, column) the adds run in
+// ascending nz order with un-fused arithmetic, like the reference's inner loop.
+__global__ void __launch_bounds__(128)
+    spmm_csr_row_warp(const int* __restrict__ offsets, const int* __restrict__ indices,
+                      const float* __restrict__ values, const float* __restrict__ B,
+                      float* __restrict__ C, int rows, int n) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + warp;
+  const int col = blockIdx.y * 32 + lane;
+  if (row >= rows) return;
+  const int begin = __ldg(offsets + row), end = __ldg(offsets + row + 1);
+  float acc = 0.0f;
+  for (int base = begin; base < end; base += 32) {
+    // one coalesced read of up to 32 (index, value) pairs, then broadcast by shuffle
+    const int mine = base + lane;
+    int idx = 0;
+    float val = 0.0f;
+    if (mine < end) { idx = __ldg(indices + mine); val = __ldg(values + mine); }
+    const int cnt = min(32, end - base);
+    for (int k = 0; k < cnt; ++k) {
+      const int i = __shfl_sync(0xffffffffu, idx, k);
+      const float v = __shfl_sync(0xffffffffu, val, k);
+      if (col < n) acc = __fadd_rn(acc, __fmul_rn(v, __ldg(B + (long long)i * n + col)));
+    }
+  }
+  if (col < n) C[(long long)row * n + col] = acc;
+}
+
 // -------------------------------------------------------------------- bcsr --
 template <int R, int C>
 __global__ void __launch_bounds__(128)

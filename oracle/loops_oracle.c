@@ -597,3 +597,13 @@ void orc_spmv_flat_partitioned(i32 rows, i32 K, const i32* off, const i32* idx, 
       y[lo] = y[lo] + p;
     }
 }
+/* algorithms/spmm/thread_mapped.cuh:28-53: per (row, col) a sequential sum over the
+ * row's atoms in ascending order; B [cols x n], C [rows x n] row-major. */
+void orc_spmm(i32 rows, i32 n, const i32* off, const i32* idx, const float* val, const float* B, float* C) {
+  for (i32 r = 0; r < rows; ++r)
+    for (i32 c = 0; c < n; ++c) {
+      volatile float sum = 0.0f;
+      for (i32 a = off[r]; a < off[r + 1]; ++a) { volatile float p = val[a] * B[(i64)idx[a] * n + c]; sum = sum + p; }
+      C[(i64)r * n + c] = sum;
+    }
+}

@@ -18,6 +18,11 @@
 #include <loops/algorithms/spmv/ell_thread_mapped.cuh>
 #include <loops/algorithms/spmv/ell_merge_path.cuh>
 #include <loops/algorithms/spmv/bcsr_thread_mapped.cuh>
+#include <loops/algorithms/spmv/csc_thread_mapped.cuh>
+#include <loops/algorithms/spmv/dia_thread_mapped.cuh>
+#include <loops/algorithms/spmv/flat_partitioned.cuh>
+#include <loops/algorithms/spmv/original.cuh>
+#include <loops/algorithms/spmm/thread_mapped.cuh>
 
 #include <cmath>
 #include <cstdio>
@@ -172,6 +177,24 @@ int main() {
       thrust::fill(yb.begin(), yb.end(), -1.0f);
       algorithms::spmv::dia_thread_mapped(dia, x, yb);
       check("algorithms::spmv::dia_thread_mapped", yb, bref);
+    }
+    {
+      // SpMM: C = A B with 5 dense columns; column j of B is x scaled by (j + 1)
+      const int n = 5;
+      matrix_t<float> B(cols, n), Cm(rows, n);
+      thrust::host_vector<float> hB(std::size_t(cols) * n);
+      for (int r = 0; r < cols; ++r)
+        for (int j = 0; j < n; ++j) hB[std::size_t(r) * n + j] = xs[r] * float(j + 1);
+      B.m_data = hB;
+      B.m_data_ptr = thrust::raw_pointer_cast(B.m_data.data());
+      algorithms::spmm::thread_mapped(csr, B, Cm);
+      thrust::host_vector<float> hC(Cm.m_data);
+      for (int j = 0; j < n; ++j) {
+        thrust::host_vector<float> colj(rows);
+        std::vector<float> refj(rows);
+        for (int r = 0; r < rows; ++r) { colj[r] = hC[std::size_t(r) * n + j]; refj[r] = ref[r] * float(j + 1); }
+        if (j == 0 || j == n - 1) check(j == 0 ? "algorithms::spmm::thread_mapped (col 0)" : "algorithms::spmm::thread_mapped (col 4)", colj, refj);
+      }
     }
     std::printf("   timer_t: %.3f ms\n", t.milliseconds());
     algorithms::spmv::work_oriented(csr, x, y);   check("algorithms::spmv::work_oriented", y, ref);

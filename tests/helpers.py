@@ -193,6 +193,13 @@ class Oracle:
         self.L.orc_spmv_flat_partitioned(rows, K, P(off), P(idx), P(val), P(x), P(y))
         return y
 
+    def spmm(self, off, idx, val, B):
+        rows, n = len(off) - 1, B.shape[1]
+        B = np.ascontiguousarray(B, np.float32)
+        out = np.zeros((rows, n), np.float32)
+        self.L.orc_spmm(rows, n, P(off), P(idx), P(val), P(B), P(out))
+        return out
+
     def spmv_coo(self, rows, row, col, val, x):
         y = np.zeros(rows, np.float32)
         self.L.orc_spmv_coo(C.c_int64(len(val)), P(row), P(col), P(val), P(x), P(y))

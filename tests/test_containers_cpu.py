@@ -45,3 +45,13 @@ def test_flat_uniform_occupancy_view():
     assert lay.base() is base
     d = lay.desc()
     assert d.pitch == 3 and d.num_tiles == 3 and d.num_atoms == 7 and d.offsets == off.data_ptr()
+
+
+def test_spmm_restatement_is_columnwise_spmv(oracle):
+    """algorithms/spmm/thread_mapped.cuh:28-53 restated: column j of A B is the
+    validator's SpMV with x = B[:, j] (same sequential order, so the same bits)."""
+    off, idx, val = random_csr(120, 90, 0.08, seed=12, empty_every=11)
+    B = np.random.default_rng(3).uniform(-2, 2, (90, 7)).astype(np.float32)
+    Cm = oracle.spmm(off, idx, val, B)
+    for j in range(7):
+        np.testing.assert_array_equal(Cm[:, j], oracle.spmv(off, idx, val, np.ascontiguousarray(B[:, j])))

@@ -156,6 +156,28 @@ def test_csc_flat_exact_inputs_and_banded_dia(oracle):
     np.testing.assert_array_equal(y.cpu().numpy(), oracle.spmv(off, idx, val, x))   # same order, un-fused
 
 
+@pytest.mark.parametrize("n", [1, 5, 32, 70])
+def test_spmm_thread_mapped(oracle, battery, n):
+    """algorithms/spmm/thread_mapped.cuh: C = A B; per (row, col) the same sequential
+    un-fused sum as the restatement -> bit-exact on any input."""
+    from loops_b200 import csr_t
+    from loops_b200.algorithms import spmm
+    rng = np.random.default_rng(n)
+    for b in battery[:6]:
+        A = csr_t(b["rows"], b["cols"], b["off"], b["idx"], b["val"])
+        B = rng.uniform(-1, 1, (b["cols"], n)).astype(np.float32)
+        Cm = torch.full((b["rows"], n), float("nan"), device="cuda")
+        spmm.thread_mapped(A, torch.as_tensor(B).cuda(), Cm)
+        np.testing.assert_array_equal(Cm.cpu().numpy(), oracle.spmm(b["off"], b["idx"], b["val"], B), err_msg=b["name"])
+    # column 0 of an SpMM with B[:, 0] = x is the SpMV
+    b = battery[0]
+    A = csr_t(b["rows"], b["cols"], b["off"], b["idx"], b["val"])
+    B = np.zeros((b["cols"], n), np.float32); B[:, 0] = b["x"]
+    Cm = torch.empty((b["rows"], n), device="cuda")
+    spmm.thread_mapped(A, torch.as_tensor(B).cuda(), Cm)
+    np.testing.assert_array_equal(Cm[:, 0].cpu().numpy(), b["y"])
+
+
 @pytest.mark.parametrize("R", [2, 3, 4])
 def test_battery_bcsr_f32(oracle, battery, R):
     """unittests/test_spmv_bcsr.cu:24-42 (2x2, 3x3) + 4x4, padded x."""
