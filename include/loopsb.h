@@ -209,6 +209,9 @@ int loopsb_spmv_bcsr4x4_bf16(loopsb_plan_t* plan, const uint16_t* values_bf16,
  * plain kernel is the better choice (x too large for the band walk to pay).
  * Returns LOOPSB_ERR_UNSUPPORTED (plan unchanged, still usable) when the
  * matrix does not fit the format or is not worth tiling. Synchronises.
+ * The copy is built ON THE DEVICE (loops_b200/csrc/tiled_build.cuh; only the
+ * row offsets cross PCIe); LOOPSB_TILED_HOST_BUILD=1 selects the host builder,
+ * which produces the same image.
  * ------------------------------------------------------------------------- */
 #define LOOPSB_TILE_FORCE 1
 
@@ -229,6 +232,14 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices,
 int loopsb_plan_untile(loopsb_plan_t* plan);
 /* LOOPSB_ERR_UNSUPPORTED when the plan holds no tiled copy. */
 int loopsb_plan_tiled_info(const loopsb_plan_t* plan, loopsb_tiled_info_t* info);
+
+/* Copy the plan's tiled image back to HOST arrays (format tests: the device
+ * builder must produce the host builder's image byte for byte). steps:
+ * (total_steps + es) * 256 words; stream_base: nb*q*warps + 1; block_begin: nb + 1.
+ * Any pointer may be NULL. Synchronises. */
+int loopsb_plan_tiled_download(const loopsb_plan_t* plan, uint32_t* host_steps,
+                               int64_t capacity_words, int32_t* host_stream_base,
+                               int32_t* host_block_begin);
 
 /* The same builder on HOST arrays, no device involved: returns the image the
  * plan would upload, for format tests. geometry = {nb,q,warps,cb,xb,es}. */

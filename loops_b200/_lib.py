@@ -89,6 +89,7 @@ SIGNATURES = {
     "loopsb_plan_probe_collect": (C.c_int, [_P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "loopsb_plan_tile_csr": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
     "loopsb_plan_untile": (C.c_int, [_P]),
+    "loopsb_plan_tiled_download": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
     "loopsb_plan_tiled_info": (C.c_int, [_P, C.POINTER(TiledInfo)]),
     "loopsb_tiled_image_build_host": (C.c_int, [C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(C.c_int32 * 6),
                                                 C.POINTER(_P)]),

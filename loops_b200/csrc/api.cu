@@ -7,6 +7,7 @@
 #include "spmv_schedules.cuh"
 #include "bcsr_tc.cuh"
 #include "spmv_tiled.cuh"
+#include "tiled_build.cuh"
 
 #include <cstdarg>
 #include <cstdlib>
@@ -303,6 +304,24 @@ int loopsb_plan_tiled_info(const loopsb_plan_t* plan, loopsb_tiled_info_t* info)
   return LOOPSB_OK;
 }
 
+int loopsb_plan_tiled_download(const loopsb_plan_t* plan, uint32_t* host_steps, int64_t capacity_words,
+                               int32_t* host_stream_base, int32_t* host_block_begin) {
+  LOOPSB_REQUIRE(plan != nullptr, "plan is null");
+  if (!plan->tiled) { set_error("the plan holds no band-tiled copy"); return LOOPSB_ERR_UNSUPPORTED; }
+  const bt::plan_data* d = plan->tiled;
+  const long long words = (d->total_steps + d->g.es) * bt::kStepWords;
+  LOOPSB_CUDA_TRY(cudaDeviceSynchronize());
+  if (host_steps) {
+    LOOPSB_REQUIRE(capacity_words >= words, "host buffer too small");
+    LOOPSB_CUDA_TRY(cudaMemcpy(host_steps, d->steps, size_t(words) * 4, cudaMemcpyDeviceToHost));
+  }
+  if (host_stream_base)
+    LOOPSB_CUDA_TRY(cudaMemcpy(host_stream_base, d->stream_base, (size_t(d->g.nstreams()) + 1) * 4, cudaMemcpyDeviceToHost));
+  if (host_block_begin)
+    LOOPSB_CUDA_TRY(cudaMemcpy(host_block_begin, d->blk_begin, (size_t(d->g.nb) + 1) * 4, cudaMemcpyDeviceToHost));
+  return LOOPSB_OK;
+}
+
 int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const float* values,
                          int32_t num_cols, int32_t flags, void* stream) {
   LOOPSB_REQUIRE(plan != nullptr, "plan is null");
@@ -341,55 +360,72 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const 
     }
   }
 
-  // The builder runs on the host (round 1): download CSR, tile, upload.
-  std::vector<int32_t> h_off, h_idx;
-  std::vector<float> h_val;
-  bt::host_image im;
+  bt::plan_data* d = new (std::nothrow) bt::plan_data();
+  if (!d) { set_error("host allocation failed"); return LOOPSB_ERR_ALLOC; }
+  auto fail = [&](int code) { bt::destroy(d); return code; };
   int rc = LOOPSB_OK;
-  try {
-    h_off.resize(size_t(rows) + 1); h_idx.resize(size_t(nnz)); h_val.resize(size_t(nnz));
-    LOOPSB_CUDA_TRY(cudaStreamSynchronize(s));
-    LOOPSB_CUDA_TRY(cudaMemcpy(h_off.data(), plan->lay.offsets, h_off.size() * 4, cudaMemcpyDeviceToHost));
-    LOOPSB_CUDA_TRY(cudaMemcpy(h_idx.data(), col_indices, h_idx.size() * 4, cudaMemcpyDeviceToHost));
-    LOOPSB_CUDA_TRY(cudaMemcpy(h_val.data(), values, h_val.size() * 4, cudaMemcpyDeviceToHost));
-    LOOPSB_REQUIRE(h_off[rows] == nnz, "offsets[rows] must equal num_atoms");
-    rc = bt::build_host(im, g, rows, num_cols, h_off.data(), h_idx.data(), h_val.data());
-  } catch (const std::bad_alloc&) {
-    set_error("host allocation failed while tiling");
-    rc = LOOPSB_ERR_ALLOC;
+  if (!getenv("LOOPSB_TILED_HOST_BUILD")) {
+    // Device builder (tiled_build.cuh): the matrix stays in HBM, only the row
+    // offsets and a few counters cross PCIe. Same image as the host builder.
+    rc = bt::build_device(d, g, rows, num_cols, plan->lay.offsets, col_indices, values, s);
+    if (rc != LOOPSB_OK) return fail(rc);
+  } else {
+    // Host builder (the reference implementation of the format; also what the
+    // CPU format tests run): download CSR, tile, upload.
+    std::vector<int32_t> h_off, h_idx;
+    std::vector<float> h_val;
+    bt::host_image im;
+    try {
+      h_off.resize(size_t(rows) + 1); h_idx.resize(size_t(nnz)); h_val.resize(size_t(nnz));
+      if (cudaStreamSynchronize(s) != cudaSuccess ||
+          cudaMemcpy(h_off.data(), plan->lay.offsets, h_off.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+          cudaMemcpy(h_idx.data(), col_indices, h_idx.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+          cudaMemcpy(h_val.data(), values, h_val.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        set_error("download of the CSR arrays failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(LOOPSB_ERR_CUDA);
+      }
+      if (h_off[rows] != nnz) { set_error("invalid argument: offsets[rows] must equal num_atoms"); return fail(LOOPSB_ERR_INVALID); }
+      rc = bt::build_host(im, g, rows, num_cols, h_off.data(), h_idx.data(), h_val.data());
+    } catch (const std::bad_alloc&) {
+      set_error("host allocation failed while tiling");
+      rc = LOOPSB_ERR_ALLOC;
+    }
+    if (rc != LOOPSB_OK) return fail(rc);
+    const size_t steps_b = im.steps.size() * 4, base_b = im.stream_base.size() * 4;
+    if (cudaMalloc(&d->steps, steps_b ? steps_b : 16) != cudaSuccess ||
+        cudaMalloc(&d->stream_base, base_b) != cudaSuccess ||
+        cudaMalloc(&d->blk_begin, im.blk_begin.size() * 4) != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("device allocation of the band-tiled copy failed (%zu bytes)", steps_b);
+      return fail(LOOPSB_ERR_ALLOC);
+    }
+    if (cudaMemcpy(d->steps, im.steps.data(), steps_b, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d->stream_base, im.stream_base.data(), base_b, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d->blk_begin, im.blk_begin.data(), im.blk_begin.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("upload of the band-tiled copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return fail(LOOPSB_ERR_CUDA);
+    }
+    d->g = im.g;
+    d->total_steps = im.total_steps; d->real_entries = im.real_entries; d->pad_entries = im.pad_entries;
+    d->flagged_entries = im.flagged_entries; d->flagged_steps = im.flagged_steps;
   }
-  if (rc != LOOPSB_OK) return rc;
-  h_idx.clear(); h_idx.shrink_to_fit(); h_val.clear(); h_val.shrink_to_fit();
-  if (!force && im.flagged_steps * 20 > im.total_steps) {
+  if (!force && d->flagged_steps * 20 > d->total_steps) {
     // rows with long runs inside a band (or too many bands per step) push steps
     // onto the general y-update path; above 5 % of the steps the plain kernel wins
     set_error("band-tiled plan not profitable (%lld of %lld steps need the general y-update path)",
-              im.flagged_steps, im.total_steps);
-    return LOOPSB_ERR_UNSUPPORTED;
+              d->flagged_steps, d->total_steps);
+    return fail(LOOPSB_ERR_UNSUPPORTED);
   }
-
-  bt::plan_data* d = new (std::nothrow) bt::plan_data();
-  if (!d) { set_error("host allocation failed"); return LOOPSB_ERR_ALLOC; }
-  d->g = im.g;
+  struct { bt::geom g; } im{d->g};   // the final geometry (row blocks cut, rb known)
   d->smem = im.g.smem_bytes();
-  auto fail = [&](int code) { bt::destroy(d); return code; };
-  const size_t steps_b = im.steps.size() * 4, base_b = im.stream_base.size() * 4;
+  const size_t steps_b = size_t(d->total_steps + im.g.es) * bt::kStepWords * 4, base_b = (size_t(im.g.nstreams()) + 1) * 4;
   const size_t part_b = im.g.q > 1 ? size_t(im.g.q) * im.g.nb * ((im.g.rb + 3) & ~3) * 4 : 0;
-  if (cudaMalloc(&d->steps, steps_b ? steps_b : 16) != cudaSuccess ||
-      cudaMalloc(&d->stream_base, base_b) != cudaSuccess ||
-      cudaMalloc(&d->blk_begin, im.blk_begin.size() * 4) != cudaSuccess ||
-      (part_b && cudaMalloc(&d->partial, part_b) != cudaSuccess) ||
-      (part_b && cudaMalloc(&d->counters, size_t(im.g.nb) * 8) != cudaSuccess)) {
-    (void)cudaGetLastError();
-    set_error("device allocation of the band-tiled copy failed (%zu bytes)", steps_b + part_b);
-    return fail(LOOPSB_ERR_ALLOC);
-  }
-  if (cudaMemcpy(d->steps, im.steps.data(), steps_b, cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMemcpy(d->stream_base, im.stream_base.data(), base_b, cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMemcpy(d->blk_begin, im.blk_begin.data(), im.blk_begin.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+  if ((part_b && cudaMalloc(&d->partial, part_b) != cudaSuccess) ||
+      (part_b && cudaMalloc(&d->counters, size_t(im.g.nb) * 8) != cudaSuccess) ||
       (part_b && cudaMemset(d->counters, 0, size_t(im.g.nb) * 8) != cudaSuccess)) {
-    set_error("upload of the band-tiled copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-    return fail(LOOPSB_ERR_CUDA);
+    (void)cudaGetLastError();
+    set_error("device allocation of the partial-row workspace failed (%zu bytes)", part_b);
+    return fail(LOOPSB_ERR_ALLOC);
   }
   if (getenv("LOOPSB_DEBUG_PHASES")) {
     if (cudaMalloc(&d->prof, (size_t(im.g.nstreams()) * 8 + size_t(im.g.grid()) * 4) * sizeof(long long)) != cudaSuccess) { (void)cudaGetLastError(); d->prof = nullptr; }
@@ -413,8 +449,6 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const 
   }
   d->key_indices = col_indices;
   d->key_values = values;
-  d->total_steps = im.total_steps; d->real_entries = im.real_entries; d->pad_entries = im.pad_entries;
-  d->flagged_entries = im.flagged_entries; d->flagged_steps = im.flagged_steps;
   d->bytes = (long long)(steps_b + base_b + part_b + (part_b ? size_t(im.g.nb) * 4 : 0));
   if (plan->tiled) bt::destroy(plan->tiled);
   plan->tiled = d;
