@@ -33,34 +33,46 @@ namespace loopsb {
 namespace sk {
 
 // ------------------------------------------------------------------ thread --
+// thread_mapped keeps the reference's map (thread g owns rows g, g+G, ...; each
+// row summed left to right by its thread -- ref thread_mapped.cuh:27-56), but the
+// 32 rows of a warp are one CONTIGUOUS range of CSR atoms, so the warp reads that
+// range coalesced (indices, values, then the x gathers, all 32 lanes wide), parks
+// the un-fused products in shared memory, and every lane then adds ITS row's
+// products in order. Same adds in the same order as one-thread-per-row (bit-exact
+// vs the CPU validator), without the per-lane strided streams.
+constexpr int kThreadChunk = 256;   // atoms staged per warp and round
+
 __global__ void __launch_bounds__(128)
     spmv_thread_mapped_csr(const int* __restrict__ offsets,
                            const int* __restrict__ indices,
                            const float* __restrict__ values,
                            const float* __restrict__ x, float* __restrict__ y,
                            int rows) {
+  __shared__ float prod[4][kThreadChunk];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int stride = gridDim.x * blockDim.x;
-  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < rows;
-       row += stride) {
-    int k = __ldg(offsets + row);
-    const int end = __ldg(offsets + row + 1);
+  // whole warps iterate together (rows beyond the end behave like empty rows)
+  for (int row0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; row0 < rows; row0 += stride) {
+    const int row = row0 + lane;
+    const int last = min(row0 + 32, rows);            // one past the warp's last row
+    const int a_end = __ldg(offsets + last);
+    const int beg = row < rows ? __ldg(offsets + row) : a_end;
+    const int end = row < rows ? __ldg(offsets + row + 1) : a_end;
+    const int a0 = __shfl_sync(0xffffffffu, beg, 0);
     float sum = 0.0f;
-    // four independent (index -> x) chains in flight, adds stay in order
-    for (; k + 4 <= end; k += 4) {
-      const int c0 = __ldg(indices + k), c1 = __ldg(indices + k + 1);
-      const int c2 = __ldg(indices + k + 2), c3 = __ldg(indices + k + 3);
-      const float v0 = __ldg(values + k), v1 = __ldg(values + k + 1);
-      const float v2 = __ldg(values + k + 2), v3 = __ldg(values + k + 3);
-      const float x0 = __ldg(x + c0), x1 = __ldg(x + c1);
-      const float x2 = __ldg(x + c2), x3 = __ldg(x + c3);
-      sum = __fadd_rn(sum, __fmul_rn(v0, x0));
-      sum = __fadd_rn(sum, __fmul_rn(v1, x1));
-      sum = __fadd_rn(sum, __fmul_rn(v2, x2));
-      sum = __fadd_rn(sum, __fmul_rn(v3, x3));
+    int cur = beg;
+    for (int base = a0; base < a_end; base += kThreadChunk) {
+#pragma unroll
+      for (int j = 0; j < kThreadChunk / 32; ++j) {
+        const int a = base + j * 32 + lane;
+        if (a < a_end) prod[warp][j * 32 + lane] = __fmul_rn(__ldg(values + a), __ldg(x + __ldg(indices + a)));
+      }
+      __syncwarp();
+      const int stop = min(end, base + kThreadChunk);
+      for (; cur < stop; ++cur) sum = __fadd_rn(sum, prod[warp][cur - base]);
+      __syncwarp();
     }
-    for (; k < end; ++k)
-      sum = __fadd_rn(sum, __fmul_rn(__ldg(values + k), __ldg(x + __ldg(indices + k))));
-    y[row] = sum;
+    if (row < rows) y[row] = sum;
   }
 }
 
