@@ -13,4 +13,6 @@ LOOPSB_TILED=0 timeout 900 ncu --set full --clock-control none --import-source o
 LOOPSB_TILED=0 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/bench_n1_plain.json 2> gpurun_out/bench_n1_plain.err; echo "bench plain rc=$?"; cut -c1-300 gpurun_out/bench_n1_plain.json
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:bcsr4x4 -s 2 -c 2 -f -o gpurun_out/prof_bcsr \
     python tools/run_bcsr.py 5 > gpurun_out/ncu_bcsr.log 2>&1; echo "ncu bcsr rc=$?"
+timeout 300 python tools/bcsr_bench.py > gpurun_out/bcsr_bench.log 2>&1; head -1 gpurun_out/bcsr_bench.log
+timeout 600 python tools/tiled_sweep.py 0,0,0,0,0,0 37,4,24,6144,4,3 37,4,20,7168,3,3 37,4,16,4096,4,3 > gpurun_out/tiled_sweep.log 2>&1; grep -v "^{" gpurun_out/tiled_sweep.log | cut -c1-200
 ls -la gpurun_out/*.ncu-rep
