@@ -204,6 +204,9 @@ int loopsb_spmv_bcsr4x4_bf16(loopsb_plan_t* plan, const uint16_t* values_bf16,
  * handed the SAME col_indices / values pointers the copy was made from (and a
  * 16-byte aligned x); any other pointers run the plain CSR kernel. If the
  * caller changes values in place it must call loopsb_plan_tile_csr again.
+ * A plan serves ONE SpMV at a time: the tiled kernel keeps per-plan partial-row
+ * and arrival-counter workspaces, so calls on the same plan must be ordered on
+ * one stream (concurrent streams need one plan each).
  *
  * flags bit 0 (LOOPSB_TILE_FORCE): build even when the cost model says the
  * plain kernel is the better choice (x too large for the band walk to pay).

@@ -207,6 +207,10 @@ int launch_tiled(bt::plan_data* d, const float* x, float* y, cudaStream_t s) {
   p.xb = d->g.xb; p.es = d->g.es; p.nband = d->g.nband; p.q = d->g.q; p.nb = d->g.nb;
   p.prof = d->prof;
   p.peers = d->peers;
+  {
+    static const int ahead = getenv("LOOPSB_TILED_L2AHEAD") ? atoi(getenv("LOOPSB_TILED_L2AHEAD")) : bt::kL2Ahead;
+    p.l2_ahead = ahead;
+  }
   bt::kernel_fn k = bt::kernel_for(d->g.warps, d->g.es, d->prof != nullptr);
   if (d->peers) {
     // every CTA resident at once (checked at plan time): the CTAs of a row block may wait for each other

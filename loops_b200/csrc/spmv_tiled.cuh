@@ -511,6 +511,7 @@ struct params {
   float* partial;       // [q][nb*rb] when q > 1
   unsigned* counters;   // [2 * nb] when q > 1 (arrivals, departures)
   int rows, cols, rb, cq, cb, xb, es, nband, q, nb;
+  int l2_ahead;         // steps between the L2 prefetch and the register prefetch
   int peers;            // 1: cooperative launch, the q CTAs of a row block share the reduction
   long long* prof;      // PROFILE builds: 8 counters per consumer warp, then 4 wall-clock stamps per CTA
 };
@@ -618,6 +619,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
 #pragma unroll
     for (int k = 0; k < DEPTH; ++k) load_step(buf[k], src + size_t(k) * kStepWords, lane);
     const uint32_t* refill = src + size_t(DEPTH) * kStepWords;  // next step to request
+    const size_t l2_ahead_words = size_t(p.l2_ahead) * kStepWords;
     // x-ring bookkeeping: ring slot / parity of the next band to acquire, and a
     // FIFO (3 bits per entry) of the slots of the bands this warp still holds.
     // What to do at each step comes from the step's control word.
@@ -727,7 +729,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
         // steps into the neighbour's stream -- the compares cost more than the loads.)
         load_step(buf[k], refill, lane);
         {
-          const uint32_t* far = refill + size_t(kL2Ahead) * kStepWords + lane * 32;
+          const uint32_t* far = refill + l2_ahead_words + lane * 32;
           if (lane < 8 && far < p.steps_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(far));
         }
         refill += kStepWords;
