@@ -222,10 +222,11 @@ typedef struct loopsb_tiled_info {
   int32_t nb, q, warps, cb, xb, es;   /* row blocks, column parts, consumer warps,
                                          band width, x-ring depth, stream-ring depth */
   int32_t rb, rw, cq, nband;          /* max rows/block, max rows/warp, columns/part, bands/part */
-  int32_t grid_blocks, cta_threads, smem_bytes, reserved;
+  int32_t grid_blocks, cta_threads, smem_bytes;
+  int32_t long_steps;                 /* steps with a run over >= 3 lanes (segmented-scan fast path) */
   int64_t total_steps;                /* 1 KB steps (128 entries) in the copy   */
   int64_t real_entries, pad_entries;  /* nnz and padding entries                */
-  int64_t flagged_entries, flagged_steps; /* same-row lane collisions (slow path) */
+  int64_t flagged_entries, flagged_steps; /* rows split into separate cell ranges (general path) */
   int64_t bytes;                      /* device memory held by the copy         */
 } loopsb_tiled_info_t;
 

@@ -63,12 +63,12 @@ class PlanInfo(C.Structure):
 class TiledInfo(C.Structure):
     """loopsb_tiled_info_t"""
     _fields_ = [(n, C.c_int32) for n in ("nb", "q", "warps", "cb", "xb", "es", "rb", "rw", "cq", "nband",
-                                         "grid_blocks", "cta_threads", "smem_bytes", "reserved")] + \
+                                         "grid_blocks", "cta_threads", "smem_bytes", "long_steps")] + \
                [(n, C.c_int64) for n in ("total_steps", "real_entries", "pad_entries", "flagged_entries",
                                          "flagged_steps", "bytes")]
 
     def as_dict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
 TILE_FORCE = 1

@@ -225,13 +225,15 @@ int launch_tiled(bt::plan_data* d, const float* x, float* y, cudaStream_t s) {
 }
 
 void fill_tiled_info(loopsb_tiled_info_t* o, const bt::geom& g, long long total_steps, long long real_entries,
-                     long long pad_entries, long long flagged_entries, long long flagged_steps, long long bytes) {
+                     long long pad_entries, long long flagged_entries, long long flagged_steps, long long bytes,
+                     long long long_steps) {
   memset(o, 0, sizeof(*o));
   o->nb = g.nb; o->q = g.q; o->warps = g.warps; o->cb = g.cb; o->xb = g.xb; o->es = g.es;
   o->rb = g.rb; o->rw = g.rw; o->cq = g.cq; o->nband = g.nband;
   o->grid_blocks = g.grid(); o->cta_threads = g.cta_threads(); o->smem_bytes = g.smem_bytes();
   o->total_steps = total_steps; o->real_entries = real_entries; o->pad_entries = pad_entries;
   o->flagged_entries = flagged_entries; o->flagged_steps = flagged_steps; o->bytes = bytes;
+  o->long_steps = int32_t(long_steps);
 }
 }  // namespace
 
@@ -270,7 +272,7 @@ int loopsb_tiled_image_info(const loopsb_tiled_image_t* img, loopsb_tiled_info_t
   LOOPSB_REQUIRE(img != nullptr && info != nullptr, "null argument");
   const bt::host_image& im = img->im;
   fill_tiled_info(info, im.g, im.total_steps, im.real_entries, im.pad_entries, im.flagged_entries,
-                  im.flagged_steps, (long long)im.steps.size() * 4);
+                  im.flagged_steps, (long long)im.steps.size() * 4, im.long_steps);
   return LOOPSB_OK;
 }
 
@@ -304,7 +306,7 @@ int loopsb_plan_tiled_info(const loopsb_plan_t* plan, loopsb_tiled_info_t* info)
   if (!plan->tiled) { set_error("the plan holds no band-tiled copy"); return LOOPSB_ERR_UNSUPPORTED; }
   const bt::plan_data* d = plan->tiled;
   fill_tiled_info(info, d->g, d->total_steps, d->real_entries, d->pad_entries, d->flagged_entries,
-                  d->flagged_steps, d->bytes);
+                  d->flagged_steps, d->bytes, d->long_steps);
   return LOOPSB_OK;
 }
 
@@ -411,7 +413,7 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const 
     }
     d->g = im.g;
     d->total_steps = im.total_steps; d->real_entries = im.real_entries; d->pad_entries = im.pad_entries;
-    d->flagged_entries = im.flagged_entries; d->flagged_steps = im.flagged_steps;
+    d->flagged_entries = im.flagged_entries; d->flagged_steps = im.flagged_steps; d->long_steps = im.long_steps;
   }
   if (!force && d->flagged_steps * 20 > d->total_steps) {
     // rows with long runs inside a band (or too many bands per step) push steps

@@ -60,11 +60,14 @@ constexpr int kStepWords = 2 * kStep;     // 256 words = 1 KB
 constexpr uint32_t kFlagBit = 0x80000000u;
 constexpr int kL2Ahead = 6;               // steps between the L2 prefetch and the register prefetch
 // Step control word (ballot of bit 31 of the slot-0 ids):
-//   bit 0       dirty: some row of the step cannot be combined by the fast path
+//   bit 0       dirty: some row of the step is NOT one contiguous range of cells (general path)
+//   bit 29      long : every row is contiguous, but some run covers three or more lanes
+//               (fast path with a segmented scan over the lanes instead of one hand-off)
 //   bits 1..12  lead : empty bands to acquire and release at once before the step
 //   bits 13..16 plen : bands that follow, first to last band STARTING in this step
 //   bits 17..24 pat  : bit i = band i of those has entries (held), 0 = empty (released at once)
 //   bits 25..28 nrel : held bands whose last entry is in this step (released after it, oldest first)
+constexpr uint32_t kMetaLongBit = 1u << 29;
 constexpr int kMetaLeadShift = 1, kMetaLeadBits = 12, kMetaPlenShift = 13, kMetaPatShift = 17, kMetaRelShift = 25;
 constexpr int kMaxRowsPerBlock = 32767;   // 15 row bits, one value kept for the scratch row
 constexpr int kMaxRingFloats = 65532;     // 16 column bits, zero word behind the ring
@@ -127,6 +130,7 @@ struct host_image {
   std::vector<int32_t> blk_begin;    // nb + 1: first row of every row block (cut by nonzero count)
   std::vector<int32_t> warp_begin;   // [cta][warps + 1]: block-local first row of every consumer warp
   long long total_steps = 0, real_entries = 0, pad_entries = 0, flagged_entries = 0, flagged_steps = 0;
+  long long long_steps = 0;   // steps whose runs need the segmented scan (contiguous, >= 3 lanes)
 };
 
 // Static split of [0, n) over the host threads (LOOPSB_HOST_THREADS, default
@@ -388,7 +392,9 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
           int lane = 0;
           while (used[lane][best]) ++lane;
           put(lane, best, e[0], true);
-        } else if (L <= kPerLane) {
+          continue;
+        }
+        if (L <= kPerLane) {
           int bl = -1, bj = -1, best_cost = 1 << 30;
           for (int lane = 0; lane < kLanes; ++lane)
             for (int j = 0; j + L <= kPerLane; ++j) {
@@ -399,37 +405,51 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
               cost += cy[j + L - 1][ybank(e[L - 1])];
               if (cost < best_cost) { best_cost = cost; bl = lane; bj = j; }
             }
-          if (bl < 0) { failed = true; break; }
-          for (int i = 0; i < L; ++i) put(bl, bj + i, e[i], i == L - 1);
-        } else {
-          // long run: whole lanes from slot 0 on, contiguous (2 lanes stay clean, more are flagged later)
-          const int lanes_needed = (L + kPerLane - 1) / kPerLane;
-          int bl = -1;
-          for (int lane = 0; lane + lanes_needed <= kLanes && bl < 0; ++lane) {
-            bool ok = true;
-            for (int i = 0; i < L; ++i) ok = ok && !used[lane + i / kPerLane][i % kPerLane];
-            if (ok) bl = lane;
+          if (bl >= 0) {
+            for (int i = 0; i < L; ++i) put(bl, bj + i, e[i], i == L - 1);
+            continue;
           }
-          if (bl < 0) { failed = true; break; }
-          for (int i = 0; i < L; ++i) put(bl + i / kPerLane, i % kPerLane, e[i], i == kPerLane - 1);
         }
+        // longer runs: lane-aligned first (a run of up to 8 then covers two lanes and the
+        // step stays on the one-hand-off path), else the first free contiguous range of
+        // cells wherever it starts -- the kernel's segmented scan handles any range
+        int c0 = -1;
+        for (int p0 = 0; p0 + L <= kStep && c0 < 0; p0 += kPerLane) {
+          bool ok = true;
+          for (int i = 0; i < L && ok; ++i) ok = !used[(p0 + i) / kPerLane][(p0 + i) % kPerLane];
+          if (ok) c0 = p0;
+        }
+        for (int p0 = 0; p0 + L <= kStep && c0 < 0; ++p0) {
+          bool ok = true;
+          for (int i = 0; i < L && ok; ++i) ok = !used[(p0 + i) / kPerLane][(p0 + i) % kPerLane];
+          if (ok) c0 = p0;
+        }
+        if (c0 < 0) { failed = true; break; }
+        for (int i = 0; i < L; ++i) put((c0 + i) / kPerLane, (c0 + i) % kPerLane, e[i], i == L - 1);
       }
-      if (failed) continue;   // keep the stream order for this step (always a legal layout)
+      if (failed) {
+        // out of room (lane alignment leaves holes): lay the units back to back in the
+        // same order instead -- every row still one contiguous range, no holes, always fits
+        for (int p = 0; p < kStep; ++p) out[p] = ent{pad_id, 0u};
+        int cell = 0;
+        for (int u : order)
+          for (int i = 0; i < unit_len[u]; ++i) out[cell++] = unit_ents[unit_start[u] + i];
+      }
       for (int p = 0; p < kStep; ++p) { w[p] = out[p].id; w[kStep + p] = out[p].val; }
     }
   });
-  // ---- pass 3: control words. A step is "clean" when every row it touches sits
-  // in ONE contiguous range of cells (cell = lane*4 + j) that spans at most two
-  // adjacent lanes -- what the kernel's fast path can combine with a per-lane run
-  // sum and one neighbour shuffle; otherwise it is marked dirty and takes the
-  // general path. The x-ring events of the step (which bands the warp must wait
+  // ---- pass 3: control words. The kernel's fast path needs every row of a step
+  // in ONE contiguous range of cells (cell = lane*4 + j): per-lane run sums, then
+  // either one neighbour hand-off (runs over at most two lanes) or a segmented
+  // scan over the lanes (bit 29: some run covers three or more lanes). A row in
+  // two separate ranges marks the step dirty (bit 0, general path). The x-ring events of the step (which bands the warp must wait
   // for before it, which it is done with after it) come from the band tables. ----
   std::vector<uint32_t> meta(size_t(total), 0u);
-  std::atomic<long long> flagged_entries(0), flagged_steps(0);
+  std::atomic<long long> flagged_entries(0), flagged_steps(0), long_steps(0);
   parallel_for(total, [&](long long step0, long long step1, int) {
     std::vector<int64_t> stamp(size_t(g.rb) + 1, -1);
     std::vector<int32_t> first(size_t(g.rb) + 1, 0), last(size_t(g.rb) + 1, 0), cnt(size_t(g.rb) + 1, 0);
-    long long fe = 0, fst = 0;
+    long long fe = 0, fst = 0, lst = 0;
     for (long long s = step0; s < step1; ++s) {
       const uint32_t* w = &im.steps[size_t(s) * kStepWords];
       for (int p = 0; p < kStep; ++p) {
@@ -438,21 +458,23 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
         if (stamp[lr] != s) { stamp[lr] = s; first[lr] = last[lr] = p; cnt[lr] = 1; }
         else { last[lr] = p; ++cnt[lr]; }
       }
-      bool any = false;
+      bool any = false, any_long = false;
       for (int p = 0; p < kStep; ++p) {
         const int lr = int((w[p] >> 16) & 0x7fff);
         if (lr == g.rb) continue;
-        const bool bad = (last[lr] - first[lr] + 1 != cnt[lr]) ||
-                         (last[lr] / kPerLane - first[lr] / kPerLane >= 2);
-        if (bad) { ++fe; any = true; }
+        if (last[lr] - first[lr] + 1 != cnt[lr]) { ++fe; any = true; }                    // not contiguous
+        else if (last[lr] / kPerLane - first[lr] / kPerLane >= 2) any_long = true;       // three or more lanes
       }
       if (any) { ++fst; meta[size_t(s)] |= 1u; }
+      if (any_long) { ++lst; meta[size_t(s)] |= kMetaLongBit; }
     }
     flagged_entries += fe;
     flagged_steps += fst;
+    long_steps += lst;
   });
   im.flagged_entries = flagged_entries.load();
   im.flagged_steps = flagged_steps.load();
+  im.long_steps = long_steps.load();
   std::atomic<int> meta_overflow(0);
   parallel_for(ns, [&](long long st0, long long st1, int) {
     for (long long st = st0; st < st1; ++st) {
@@ -544,6 +566,60 @@ struct step_regs {
 __device__ __forceinline__ void load_step(step_regs& r, const uint32_t* step, int lane) {
   r.I = __ldcs(reinterpret_cast<const uint4*>(step) + lane);
   r.V = __ldcs(reinterpret_cast<const float4*>(step + kStep) + lane);
+}
+
+// Long runs: what lane l receives from the lanes after it. T_l = S_l + C_l * T_{l+1}
+// is what lane l hands down -- its own head-run sum S_l plus, when the whole lane is
+// one run that came from above (C_l), everything that passes through it; lane l
+// receives T_{l+1}. A segmented suffix scan over the 32 lanes (5 shuffle rounds).
+__device__ __forceinline__ float long_run_recv(float S, bool C) {
+  const int lane = threadIdx.x & 31;
+  float T = S;
+  bool P = C;
+#pragma unroll
+  for (int dd = 1; dd < 32; dd <<= 1) {
+    const float Td = __shfl_down_sync(0xffffffffu, T, dd);
+    const bool Pd = __shfl_down_sync(0xffffffffu, int(P), dd) != 0;
+    if (lane + dd < 32) { if (P) T += Td; P = P & Pd; }
+  }
+  return __shfl_down_sync(0xffffffffu, T, 1);
+}
+
+// The two rare kinds of step, kept out of line so the hot loop stays small:
+//  * dirty (a row in separate cell ranges): slot by slot through rmw_general;
+//  * long runs (every row contiguous, some over three or more lanes): the fast
+//    path's arithmetic with the segmented scan in place of the single hand-off.
+__device__ __noinline__ void cold_update(float* ys, int r0, int r1, int r2, int r3, float p0, float p1, float p2,
+                                         float p3, int scratch, bool non_contiguous) {
+  if (non_contiguous) {
+    rmw_general(ys, r0, p0, scratch);
+    rmw_general(ys, r1, p1, scratch);
+    rmw_general(ys, r2, p2, scratch);
+    rmw_general(ys, r3, p3, scratch);
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  const bool c1 = r1 == r0, c2 = r2 == r1, c3 = r3 == r2;
+  const float v0 = p0;
+  const float v1 = c1 ? v0 + p1 : p1;
+  const float v2 = c2 ? v1 + p2 : p2;
+  float v3 = c3 ? v2 + p3 : p3;
+  const int prev_last = __shfl_up_sync(0xffffffffu, r3, 1);
+  const bool hc = (lane > 0) & (prev_last == r0);
+  const bool h0 = !c1, h1 = c1 & !c2, h2 = c1 & c2 & !c3, h3 = c1 & c2 & c3;
+  const float hv = h0 ? v0 : (h1 ? v1 : (h2 ? v2 : v3));
+  float recv = long_run_recv(hc ? hv : 0.f, hc & h3);
+  recv = lane == 31 ? 0.f : recv;
+  v3 += recv;
+  const int a0 = (!c1 & !(hc & h0)) ? r0 : scratch;
+  const int a1 = (!c2 & !(hc & h1)) ? r1 : scratch;
+  const int a2 = (!c3 & !(hc & h2)) ? r2 : scratch;
+  const int a3 = !(hc & h3) ? r3 : scratch;
+  const float y0 = ys[a0], y1 = ys[a1], y2 = ys[a2], y3 = ys[a3];
+  ys[a0] = y0 + v0;
+  ys[a1] = y1 + v1;
+  ys[a2] = y2 + v2;
+  ys[a3] = y3 + v3;
 }
 
 template <int WARPS, int DEPTH, bool PROFILE = false>
@@ -682,12 +758,12 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
         const float p3 = __fmul_rn(V.w, xs[I.w & 0xffffu]);
         const int r0 = int((I.x >> 16) & 0x7fffu), r1 = int((I.y >> 16) & 0x7fffu);
         const int r2 = int((I.z >> 16) & 0x7fffu), r3 = int((I.w >> 16) & 0x7fffu);
-        const bool dirty = (m & 1u) != 0u;
+        const bool dirty = (m & (1u | kMetaLongBit)) != 0u;   // anything but the one-hand-off fast path
         if (PROFILE) { const long long t1 = clock64(); t_gather += (p0 + p1 + p2 + p3 == 12345.f) ? 1 : t1 - t0; t0 = t1; }
         if (!dirty) {
-          // Clean step: a row's entries are one contiguous slot range over at most
-          // two adjacent lanes. Sum runs inside the lane, hand a run that started in
-          // the previous lane to that lane, then update distinct y rows independently.
+          // Every row of the step is one contiguous range of cells. Sum runs inside the
+          // lane, hand the part of a run that lies in later lanes back to the lane where
+          // the run starts, then update distinct y rows independently.
           const bool c1 = r1 == r0, c2 = r2 == r1, c3 = r3 == r2;
           const float v0 = p0;
           const float v1 = c1 ? v0 + p1 : p1;
@@ -698,7 +774,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
           // slot that closes the lane's FIRST run (exactly one of h0..h3 is set)
           const bool h0 = !c1, h1 = c1 & !c2, h2 = c1 & c2 & !c3, h3 = c1 & c2 & c3;
           const float hv = h0 ? v0 : (h1 ? v1 : (h2 ? v2 : v3));
-          float recv = __shfl_down_sync(0xffffffffu, hc ? hv : 0.f, 1);
+          float recv = __shfl_down_sync(0xffffffffu, hc ? hv : 0.f, 1);   // runs end in the next lane at the latest
           recv = lane == 31 ? 0.f : recv;
           v3 += recv;
           // a slot writes y when it closes a run that this lane owns; everything
@@ -713,10 +789,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
           ys[a2] = y2 + v2;
           ys[a3] = y3 + v3;
         } else {
-          rmw_general(ys, r0, p0, scratch);
-          rmw_general(ys, r1, p1, scratch);
-          rmw_general(ys, r2, p2, scratch);
-          rmw_general(ys, r3, p3, scratch);
+          cold_update(ys, r0, r1, r2, r3, p0, p1, p2, p3, scratch, (m & 1u) != 0u);
           if (PROFILE) ++n_slow;
         }
         if (PROFILE) t_rmw += clock64() - t0;
@@ -855,6 +928,7 @@ struct plan_data {
   const void* key_indices = nullptr;  // the CSR arrays this copy was made from
   const void* key_values = nullptr;
   long long total_steps = 0, real_entries = 0, pad_entries = 0, flagged_entries = 0, flagged_steps = 0;
+  long long long_steps = 0;
   long long bytes = 0;
   int smem = 0;
   int peers = 0;   // the grid fits the device in one wave: launch cooperatively, share the q-way reduction

@@ -245,7 +245,7 @@ struct pack_smem {
 
 __global__ void __launch_bounds__(kPackThreads)
     pack_kernel(uint32_t* __restrict__ steps, long long total_steps, const uint32_t* __restrict__ meta, int rb,
-                uint32_t pad_id, int do_pack, unsigned long long* __restrict__ stats /* flagged entries, steps */) {
+                uint32_t pad_id, int do_pack, unsigned long long* __restrict__ stats /* dirty entries, dirty steps, long-run steps */) {
   extern __shared__ __align__(16) unsigned char pk_raw[];
   pack_smem& sm = *reinterpret_cast<pack_smem*>(pk_raw);
   const int t = threadIdx.x;
@@ -313,7 +313,9 @@ __global__ void __launch_bounds__(kPackThreads)
         int lane = 0;
         while (sm.used[lane][t] & (1u << best)) ++lane;
         put(lane, best, id, ent_val(u, 0), true);
-      } else if (L <= kPerLane) {
+        continue;
+      }
+      if (L <= kPerLane) {
         int bl = -1, bj = -1, best_cost = 1 << 30;
         for (int lane = 0; lane < kLanes; ++lane)
           for (int j = 0; j + L <= kPerLane; ++j) {
@@ -327,26 +329,45 @@ __global__ void __launch_bounds__(kPackThreads)
             cost += sm.cy[j + L - 1][(ent_id(u, L - 1) >> 16) & 31u][t];
             if (cost < best_cost) { best_cost = cost; bl = lane; bj = j; }
           }
-        if (bl < 0) { failed = true; break; }
-        for (int i = 0; i < L; ++i) put(bl, bj + i, ent_id(u, i), ent_val(u, i), i == L - 1);
-      } else {
-        const int lanes_needed = (L + kPerLane - 1) / kPerLane;
-        int bl = -1;
-        for (int lane = 0; lane + lanes_needed <= kLanes && bl < 0; ++lane) {
-          bool ok = true;
-          for (int i = 0; i < L; ++i) ok = ok && !(sm.used[lane + i / kPerLane][t] & (1u << (i % kPerLane)));
-          if (ok) bl = lane;
+        if (bl >= 0) {
+          for (int i = 0; i < L; ++i) put(bl, bj + i, ent_id(u, i), ent_val(u, i), i == L - 1);
+          continue;
         }
-        if (bl < 0) { failed = true; break; }
-        for (int i = 0; i < L; ++i) put(bl + i / kPerLane, i % kPerLane, ent_id(u, i), ent_val(u, i), i == kPerLane - 1);
+      }
+      // longer runs: lane-aligned first, else the first free contiguous range of cells
+      int c0 = -1;
+      for (int p0 = 0; p0 + L <= kStep && c0 < 0; p0 += kPerLane) {
+        bool ok = true;
+        for (int i = 0; i < L && ok; ++i) ok = !(sm.used[(p0 + i) / kPerLane][t] & (1u << ((p0 + i) % kPerLane)));
+        if (ok) c0 = p0;
+      }
+      for (int p0 = 0; p0 + L <= kStep && c0 < 0; ++p0) {
+        bool ok = true;
+        for (int i = 0; i < L && ok; ++i) ok = !(sm.used[(p0 + i) / kPerLane][t] & (1u << ((p0 + i) % kPerLane)));
+        if (ok) c0 = p0;
+      }
+      if (c0 < 0) { failed = true; break; }
+      for (int i = 0; i < L; ++i) put((c0 + i) / kPerLane, (c0 + i) % kPerLane, ent_id(u, i), ent_val(u, i), i == L - 1);
+    }
+    if (failed) {
+      // out of room: lay the units back to back in the same order (always fits)
+      for (int p = 0; p < kStep; ++p) { sm.out_id[p][t] = pad_id; sm.out_val[p][t] = 0u; }
+      int cell = 0;
+      for (int oi = 0; oi < no; ++oi) {
+        const int u = sm.order[oi][t];
+        for (int i = 0; i < int(sm.unit_len[u][t]); ++i) {
+          sm.out_id[cell][t] = ent_id(u, i);
+          sm.out_val[cell][t] = ent_val(u, i);
+          ++cell;
+        }
       }
     }
-    packed = !failed;
+    packed = true;
   }
   // the final cell contents are in out_* when packed, in in_* otherwise
   // ---- dirty check: every row one contiguous range of cells over at most two lanes ----
   unsigned long long flagged_entries = 0;
-  bool any = false;
+  bool any = false, any_long = false;
   for (int p = 0; p < kStep; ++p) {
     const uint32_t id = packed ? sm.out_id[p][t] : sm.in_id[p][t];
     const int lr = int((id >> 16) & 0x7fff);
@@ -356,9 +377,10 @@ __global__ void __launch_bounds__(kPackThreads)
       const uint32_t ie = packed ? sm.out_id[e][t] : sm.in_id[e][t];
       if (int((ie >> 16) & 0x7fff) == lr) { if (e < first) first = e; if (e > last) last = e; ++cnt; }
     }
-    if ((last - first + 1 != cnt) || (last / kPerLane - first / kPerLane >= 2)) { ++flagged_entries; any = true; }
+    if (last - first + 1 != cnt) { ++flagged_entries; any = true; }
+    else if (last / kPerLane - first / kPerLane >= 2) any_long = true;
   }
-  const uint32_t m = meta[s] | (any ? 1u : 0u);
+  const uint32_t m = meta[s] | (any ? 1u : 0u) | (any_long ? kMetaLongBit : 0u);
   // ---- write back: cells, then bit `lane` of the control word into slot 0 of lane `lane` ----
   for (int p = 0; p < kStep; ++p) {
     uint32_t id = packed ? sm.out_id[p][t] : sm.in_id[p][t];
@@ -367,6 +389,7 @@ __global__ void __launch_bounds__(kPackThreads)
     w[kStep + p] = packed ? sm.out_val[p][t] : sm.in_val[p][t];
   }
   if (any) { atomicAdd(stats + 0, flagged_entries); atomicAdd(stats + 1, 1ull); }
+  if (any_long) atomicAdd(stats + 2, 1ull);
 }
 
 }  // namespace dev
@@ -433,7 +456,7 @@ inline int build_device(plan_data* d, geom g, int rows, int cols, const int* d_o
       cudaMalloc(&flags, 16) != cudaSuccess || cudaMalloc(&keys, n1 * 4) != cudaSuccess ||
       cudaMalloc(&atoms, n1 * 4) != cudaSuccess || cudaMalloc(&skeys, n1 * 4) != cudaSuccess ||
       cudaMalloc(&satoms, n1 * 4) != cudaSuccess || cudaMalloc(&fs, nkeys * 2) != cudaSuccess ||
-      cudaMalloc(&le, nkeys * 2) != cudaSuccess || cudaMalloc(&stats, 16) != cudaSuccess ||
+      cudaMalloc(&le, nkeys * 2) != cudaSuccess || cudaMalloc(&stats, 32) != cudaSuccess ||
       cudaMalloc(&d->blk_begin, blk_begin.size() * 4) != cudaSuccess ||
       cudaMalloc(&d->stream_base, (size_t(ns) + 1) * 4) != cudaSuccess)
     return fail(LOOPSB_ERR_ALLOC, "cudaMalloc");
@@ -441,7 +464,7 @@ inline int build_device(plan_data* d, geom g, int rows, int cols, const int* d_o
   cudaMemcpyAsync(flags, h_flags, 16, cudaMemcpyHostToDevice, s);
   cudaMemcpyAsync(d->blk_begin, blk_begin.data(), blk_begin.size() * 4, cudaMemcpyHostToDevice, s);
   cudaMemsetAsync(count, 0, nkeys * 4, s);
-  cudaMemsetAsync(stats, 0, 16, s);
+  cudaMemsetAsync(stats, 0, 32, s);
 
   dev::rowpart_kernel<<<(rows + 127) / 128, 128, 0, s>>>(d_off, d_idx, rows, cols, g.q, g.cq, rowpart, flags + 0);
   dev::warp_map_kernel<<<g.grid(), 256, 0, s>>>(rowpart, d->blk_begin, gc, wmap);
@@ -497,8 +520,8 @@ inline int build_device(plan_data* d, geom g, int rows, int cols, const int* d_o
     dev::pack_kernel<<<unsigned((total + dev::kPackThreads - 1) / dev::kPackThreads), dev::kPackThreads,
                        sizeof(dev::pack_smem), s>>>(d->steps, total, meta, g.rb, pad_id, g.pack, stats);
   }
-  unsigned long long h_stats[2] = {0, 0};
-  cudaMemcpyAsync(h_stats, stats, 16, cudaMemcpyDeviceToHost, s);
+  unsigned long long h_stats[4] = {0, 0, 0, 0};
+  cudaMemcpyAsync(h_stats, stats, 32, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(h_flags2, flags, 16, cudaMemcpyDeviceToHost, s);
   if (cudaStreamSynchronize(s) != cudaSuccess || cudaGetLastError() != cudaSuccess) return fail(LOOPSB_ERR_CUDA, "scatter / pack pass");
   if (h_flags2[2]) {
@@ -512,6 +535,7 @@ inline int build_device(plan_data* d, geom g, int rows, int cols, const int* d_o
   d->pad_entries = total * kStep - nnz;
   d->flagged_entries = (long long)h_stats[0];
   d->flagged_steps = (long long)h_stats[1];
+  d->long_steps = (long long)h_stats[2];
   return LOOPSB_OK;
 }
 

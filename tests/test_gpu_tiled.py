@@ -74,12 +74,12 @@ def test_random_exact(oracle, geometry, shape):
     np.testing.assert_array_equal(y, oracle.spmv(off, idx, val, x))
 
 
-def test_dense_rows_take_the_flagged_path(oracle):
+def test_dense_rows_take_the_long_run_path(oracle):
     off, idx, val = random_csr(64, 2000, 0.01, seed=5, heavy_row=(3, 2000), exact=True)
     x = oracle.x_recipe_int(2000)
     for geometry in [(2, 1, 4, 512, 2, 2), (2, 2, 8, 128, 2, 3), None]:
         y, info = _run(off, idx, val, x, 64, 2000, geometry, repeat=2, want_info=True)
-        assert info["flagged_entries"] > 0
+        assert info["long_steps"] > 0 and info["flagged_entries"] == 0
         np.testing.assert_array_equal(y, oracle.spmv(off, idx, val, x))
 
 
@@ -171,3 +171,15 @@ def test_full_size_config2_tiled_equals_plain():
         assert torch.equal(y, y_plain)
     info = A.plan(_lib.SCHED_MERGE_PATH_FLAT, tiled="auto").tiled_info()
     assert info is not None and info["flagged_steps"] * 20 <= info["total_steps"]
+
+
+def test_dirty_steps_take_the_general_path(oracle, monkeypatch):
+    """Packer off: rows seen in two separate cell ranges of a step set the dirty bit
+    and go through the match.any path; results stay exact."""
+    monkeypatch.setenv("LOOPSB_TILED_PACK", "0")
+    off, idx, val = random_csr(80, 640, 0.3, seed=9, exact=True)
+    x = oracle.x_recipe_int(640)
+    for geometry in [(1, 1, 4, 8, 2, 2), (2, 2, 8, 16, 3, 2)]:
+        y, info = _run(off, idx, val, x, 80, 640, geometry, repeat=2, want_info=True)
+        assert info["flagged_steps"] > 0
+        np.testing.assert_array_equal(y, oracle.spmv(off, idx, val, x))

@@ -49,7 +49,7 @@ def _compare(off, idx, val, rows, cols, geometry):
     assert rc == 0
     h = img["g"]
     for k in ("rb", "cq", "nband", "total_steps", "real_entries", "pad_entries", "flagged_entries", "flagged_steps",
-              "smem_bytes"):
+              "long_steps", "smem_bytes"):
         assert info[k] == h[k], (k, info[k], h[k])
     np.testing.assert_array_equal(blk, img["blk_begin"])
     np.testing.assert_array_equal(base, img["stream_base"])
@@ -78,7 +78,7 @@ def test_dense_rows_and_empty_bands():
     off, idx, val = random_csr(64, 2000, 0.01, seed=5, heavy_row=(3, 2000))
     for geometry in [(2, 1, 4, 512, 2, 2), (2, 2, 8, 128, 2, 3), None]:
         info = _compare(off, idx, val, 64, 2000, geometry)
-        assert info["flagged_entries"] > 0
+        assert info["long_steps"] > 0
     rows, cols = 96, 512
     rng = np.random.default_rng(11)
     o, i, v = [0], [], []
@@ -116,3 +116,10 @@ def test_host_builder_switch_gives_the_same_image(monkeypatch):
     np.testing.assert_array_equal(a[1], b[1])
     np.testing.assert_array_equal(a[2], b[2])
     np.testing.assert_array_equal(a[3], b[3])
+
+
+def test_unpacked_dirty_images_match(monkeypatch):
+    monkeypatch.setenv("LOOPSB_TILED_PACK", "0")
+    off, idx, val = random_csr(80, 640, 0.3, seed=9)
+    info = _compare(off, idx, val, 80, 640, (1, 1, 4, 8, 2, 2))
+    assert info["flagged_steps"] > 0

@@ -34,7 +34,8 @@ def _check(lib, oracle, rows, cols, off, idx, val, x, geometry, expect_flags=Non
     ref = oracle.spmv(off, idx, val, x)
     np.testing.assert_array_equal(y, ref)
     if expect_flags is not None:
-        assert (g["flagged_entries"] > 0) == expect_flags
+        assert (g["long_steps"] > 0) == expect_flags
+        assert g["flagged_entries"] == 0        # the packer keeps every row in one range of cells
     return img
 
 
@@ -62,8 +63,8 @@ def test_random_exact(lib, oracle, geometry, shape):
 
 
 def test_dense_rows_set_flags(lib, oracle):
-    """Rows much longer than a lane's 4 entries inside one band: lanes collide on
-    the row at the same slot, the builder must flag every later holder."""
+    """Rows much longer than a lane's 4 entries inside one band: their runs cover
+    three or more lanes, the step must carry the long-run bit (segmented scan)."""
     off, idx, val = random_csr(40, 300, 0.02, seed=5, heavy_row=(3, 300), exact=True)
     x = oracle.x_recipe_int(300)
     _check(lib, oracle, 40, 300, off, idx, val, x, (2, 1, 2, 128, 2, 2), expect_flags=True)
@@ -139,3 +140,14 @@ def test_powerlaw_sample_of_the_bench_workload(lib, oracle):
     x = g.x_recipe(cols).numpy()
     img = _check(lib, oracle, rows, cols, off, idx, val, x, (2, 2, 8, 512, 2, 2))
     assert img["g"]["pad_entries"] < 0.1 * rows * 32
+
+
+def test_unpacked_steps_can_be_dirty(lib, oracle, monkeypatch):
+    """With the packer off, a step that holds the tail of one band and the head of
+    the next can see a row twice in separate cell ranges: the dirty bit (general
+    y-update path) must be set, and the emulated result must still be right."""
+    monkeypatch.setenv("LOOPSB_TILED_PACK", "0")
+    off, idx, val = random_csr(20, 64, 0.5, seed=9, exact=True)
+    x = oracle.x_recipe_int(64)
+    img = _check(lib, oracle, 20, 64, off, idx, val, x, (1, 1, 1, 8, 2, 2))
+    assert img["g"]["flagged_entries"] > 0 and img["g"]["flagged_steps"] > 0

@@ -123,31 +123,24 @@ def emulate(img, x, rows, cols):
                 for i in range(128):
                     if not pad[i]:
                         slots_of.setdefault(int(lr[i]), []).append(i)
-                bad_rows = {r for r, sl in slots_of.items()
-                            if sl[-1] - sl[0] + 1 != len(sl) or sl[-1] // 4 - sl[0] // 4 >= 2}
+                bad_rows = {r for r, sl in slots_of.items() if sl[-1] - sl[0] + 1 != len(sl)}
+                long_rows = {r for r, sl in slots_of.items()
+                             if r not in bad_rows and sl[-1] // 4 - sl[0] // 4 >= 2}
                 assert dirty == bool(bad_rows), ("dirty bit mismatch", cta, w, s)
+                assert bool(meta & (1 << 29)) == bool(long_rows), ("long-run bit mismatch", cta, w, s)
                 if not dirty:
-                    # clean step, the kernel's order: run sums inside a lane, a run that
-                    # started in the previous lane is handed to it, one update per run
-                    v = prod.copy()
-                    for i in range(128):
-                        if i % 4 and lr[i] == lr[i - 1]:
-                            v[i] = np.float32(v[i - 1] + prod[i])
-                    send = np.zeros(32, np.float32)
-                    own = np.ones(128, bool)
-                    for i in range(128):
-                        if i % 4 != 3 and lr[i + 1] == lr[i]:
-                            own[i] = False
-                    for lane in range(1, 32):
-                        if lr[4 * lane] == lr[4 * lane - 1]:
-                            h = next(i for i in range(4 * lane, 4 * lane + 4) if own[i])
-                            send[lane] = v[h]
-                            own[h] = False
-                    for lane in range(31):
-                        v[4 * lane + 3] = np.float32(v[4 * lane + 3] + send[lane + 1])
-                    for i in range(128):
-                        if own[i]:
-                            ys[lr[i]] = np.float32(ys[lr[i]] + v[i])
+                    # fast path: run sums inside a lane; the parts of a run in later lanes are
+                    # handed back to the lane where the run starts, which updates y once
+                    for r, sl in slots_of.items():
+                        lane_sums = {}
+                        for i in sl:
+                            lane_sums[i // 4] = np.float32(lane_sums.get(i // 4, np.float32(0)) + prod[i]) \
+                                if (i // 4) in lane_sums else prod[i]
+                        lanes = sorted(lane_sums)
+                        rest = np.float32(0)
+                        for ln in reversed(lanes[1:]):
+                            rest = np.float32(lane_sums[ln] + rest)
+                        ys[r] = np.float32(ys[r] + np.float32(lane_sums[lanes[0]] + rest))
                 else:
                     # dirty step: slot by slot, equal rows applied in lane order
                     for j in range(4):

@@ -47,6 +47,10 @@ def time_b2b_ms(fn, warm=5, reps=100):
 
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    dmax = 1024
+    for a in sys.argv[1:]:
+        if a.startswith("--dmax="):
+            dmax = int(a.split("=")[1])   # heaviest row of the power law (hub rows exercise the long-run path)
     small = "--small" in sys.argv
     rows = cols = (1 << 16) if small else (1 << 20)
     nnz = rows * 32
@@ -56,7 +60,7 @@ def main():
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    off, idx, val = g.synth_csr(rows, cols, nnz, device="cuda")
+    off, idx, val = g.synth_csr(rows, cols, nnz, device="cuda", d_max=dmax)
     x = g.x_recipe(cols, device="cuda")
     A0 = csr_t.from_tensors(rows, cols, off, idx, val)
     y0 = torch.empty(rows, device="cuda")
