@@ -211,6 +211,8 @@ int launch_tiled(bt::plan_data* d, const float* x, float* y, cudaStream_t s) {
   {
     static const int ahead = getenv("LOOPSB_TILED_L2AHEAD") ? atoi(getenv("LOOPSB_TILED_L2AHEAD")) : bt::kL2Ahead;
     p.l2_ahead = ahead;
+    static const int guard = getenv("LOOPSB_TILED_L2GUARD") ? atoi(getenv("LOOPSB_TILED_L2GUARD")) : 0;
+    p.l2_guard = guard;
   }
   bt::kernel_fn k = bt::kernel_for(d->g.warps, d->g.es, d->prof != nullptr);
   if (d->peers) {

@@ -534,6 +534,7 @@ struct params {
   unsigned* counters;   // [2 * nb] when q > 1 (arrivals, departures)
   int rows, cols, rb, cq, cb, xb, es, nband, q, nb;
   int l2_ahead;         // steps between the L2 prefetch and the register prefetch
+  int l2_guard;         // 1: the L2 prefetch stops at the end of the warp's own stream
   int peers;            // 1: cooperative launch, the q CTAs of a row block share the reduction
   long long* prof;      // PROFILE builds: 8 counters per consumer warp, then 4 wall-clock stamps per CTA
 };
@@ -696,6 +697,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
     for (int k = 0; k < DEPTH; ++k) load_step(buf[k], src + size_t(k) * kStepWords, lane);
     const uint32_t* refill = src + size_t(DEPTH) * kStepWords;  // next step to request
     const size_t l2_ahead_words = size_t(p.l2_ahead) * kStepWords;
+    const uint32_t* l2_end = p.l2_guard ? src + size_t(nsteps) * kStepWords : p.steps_end;   // A/B: stop the L2 prefetch at the stream's end
     // x-ring bookkeeping: ring slot / parity of the next band to acquire, and a
     // FIFO (3 bits per entry) of the slots of the bands this warp still holds.
     // What to do at each step comes from the step's control word.
@@ -797,13 +799,14 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
         release(int(m >> kMetaRelShift) & 0xf);
         // step s + DEPTH into the registers just freed, and step s + DEPTH + kL2Ahead
         // from HBM into L2 (eight 128-byte lines, one per lane 0..7) so that the
-        // register prefetch only pays an L2 hit. (Stopping both at the end of the
-        // warp's own stream was measured: ~3 % slower than letting them run a few
-        // steps into the neighbour's stream -- the compares cost more than the loads.)
+        // register prefetch only pays an L2 hit. (Stopping them at the end of the warp's
+        // own stream was measured twice -- both prefetches, and the L2 one alone via
+        // LOOPSB_TILED_L2GUARD=1: ~3 % slower either way. Running a few steps into the
+        // neighbour's stream leaves the head of the streams in L2 for the next launch.)
         load_step(buf[k], refill, lane);
         {
           const uint32_t* far = refill + l2_ahead_words + lane * 32;
-          if (lane < 8 && far < p.steps_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(far));
+          if (lane < 8 && far < l2_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(far));
         }
         refill += kStepWords;
       }
