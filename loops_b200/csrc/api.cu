@@ -466,22 +466,22 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const 
               d->flagged_steps, d->total_steps);
     return fail(LOOPSB_ERR_UNSUPPORTED);
   }
-  struct { bt::geom g; } im{d->g};   // the final geometry (row blocks cut, rb known)
-  d->smem = im.g.smem_bytes();
-  const size_t steps_b = size_t(d->total_steps + im.g.es) * bt::kStepWords * 4, base_b = (size_t(im.g.nstreams()) + 1) * 4;
-  const size_t part_b = im.g.q > 1 ? size_t(im.g.q) * im.g.nb * ((im.g.rb + 3) & ~3) * 4 : 0;
+  const bt::geom& fg = d->g;   // the final geometry (row blocks cut, rb known)
+  d->smem = fg.smem_bytes();
+  const size_t steps_b = size_t(d->total_steps + fg.es) * bt::kStepWords * 4, base_b = (size_t(fg.nstreams()) + 1) * 4;
+  const size_t part_b = fg.q > 1 ? size_t(fg.q) * fg.nb * ((fg.rb + 3) & ~3) * 4 : 0;
   if ((part_b && cudaMalloc(&d->partial, part_b) != cudaSuccess) ||
-      (part_b && cudaMalloc(&d->counters, size_t(im.g.nb) * 8) != cudaSuccess) ||
-      (part_b && cudaMemset(d->counters, 0, size_t(im.g.nb) * 8) != cudaSuccess)) {
+      (part_b && cudaMalloc(&d->counters, size_t(fg.nb) * 8) != cudaSuccess) ||
+      (part_b && cudaMemset(d->counters, 0, size_t(fg.nb) * 8) != cudaSuccess)) {
     (void)cudaGetLastError();
     set_error("device allocation of the partial-row workspace failed (%zu bytes)", part_b);
     return fail(LOOPSB_ERR_ALLOC);
   }
   if (getenv("LOOPSB_DEBUG_PHASES")) {
-    if (cudaMalloc(&d->prof, (size_t(im.g.nstreams()) * 8 + size_t(im.g.grid()) * 4) * sizeof(long long)) != cudaSuccess) { (void)cudaGetLastError(); d->prof = nullptr; }
-    else cudaMemset(d->prof, 0, (size_t(im.g.nstreams()) * 8 + size_t(im.g.grid()) * 4) * sizeof(long long));
+    if (cudaMalloc(&d->prof, (size_t(fg.nstreams()) * 8 + size_t(fg.grid()) * 4) * sizeof(long long)) != cudaSuccess) { (void)cudaGetLastError(); d->prof = nullptr; }
+    else cudaMemset(d->prof, 0, (size_t(fg.nstreams()) * 8 + size_t(fg.grid()) * 4) * sizeof(long long));
   }
-  bt::kernel_fn k = bt::kernel_for(im.g.warps, im.g.es, d->prof != nullptr);
+  bt::kernel_fn k = bt::kernel_for(fg.warps, fg.es, d->prof != nullptr);
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem) != cudaSuccess) {
     set_error("cannot opt in to %d bytes of dynamic shared memory", d->smem);
     (void)cudaGetLastError();
@@ -491,15 +491,15 @@ int loopsb_plan_tile_csr(loopsb_plan_t* plan, const int32_t* col_indices, const 
     // one wave? then the launch can be cooperative and the q CTAs of a row block share the reduction
     int per_sm = 0, coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, plan->device);
-    if (coop && im.g.q > 1 && !getenv("LOOPSB_TILED_NO_PEERS") &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, im.g.cta_threads(), size_t(d->smem)) == cudaSuccess &&
-        per_sm * dp->sm_count >= im.g.grid())
+    if (coop && fg.q > 1 && !getenv("LOOPSB_TILED_NO_PEERS") &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, fg.cta_threads(), size_t(d->smem)) == cudaSuccess &&
+        per_sm * dp->sm_count >= fg.grid())
       d->peers = 1;
     (void)cudaGetLastError();
   }
   d->key_indices = col_indices;
   d->key_values = values;
-  d->bytes = (long long)(steps_b + base_b + part_b + (part_b ? size_t(im.g.nb) * 4 : 0));
+  d->bytes = (long long)(steps_b + base_b + part_b + (part_b ? size_t(fg.nb) * 8 : 0));
   if (plan->tiled) bt::destroy(plan->tiled);
   plan->tiled = d;
   return LOOPSB_OK;
