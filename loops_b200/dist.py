@@ -34,6 +34,24 @@ def nnz_imbalance(off: np.ndarray, world: int) -> float:
     return max(per) / (sum(per) / world) if sum(per) else 1.0
 
 
+def split_columns(off: torch.Tensor, idx: torch.Tensor, val: torch.Tensor, c0: int, c1: int):
+    """Split a shard by column range: entries with c0 <= col < c1 (the columns of the
+    rank's OWN x shard, rebased to 0) and the rest (global column ids). CSR order is
+    kept inside both parts, so  y = A_own @ x_shard + A_rest @ x_full  and the first
+    product does not have to wait for the all-gather. Works on CPU and CUDA tensors."""
+    rows = off.numel() - 1
+    nnz = idx.numel()
+    own = (idx >= c0) & (idx < c1)
+    rowid = torch.repeat_interleave(torch.arange(rows, device=idx.device), (off[1:] - off[:-1]).long(),
+                                    output_size=nnz)
+    cnt = torch.zeros(rows, dtype=torch.int64, device=idx.device).index_add_(0, rowid, own.long())
+    own_off = torch.zeros(rows + 1, dtype=torch.int64, device=idx.device)
+    torch.cumsum(cnt, 0, out=own_off[1:])
+    rest_off = off.long() - own_off
+    return ((own_off.to(torch.int32), (idx[own] - c0).to(torch.int32), val[own]),
+            (rest_off.to(torch.int32), idx[~own].contiguous(), val[~own].contiguous()))
+
+
 class DistSpMV:
     """y_shard = A_shard @ allgather(x_shard). `local` is this rank's csr_t
     (rows = its row range, cols = global); `x_full` is a persistent buffer."""

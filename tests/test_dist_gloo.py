@@ -48,6 +48,18 @@ def _worker(rank, world, port, q):
         y_shard = oracle.spmv(l_off, np.ascontiguousarray(l_idx), np.ascontiguousarray(l_val), x_full.numpy())
         np.testing.assert_array_equal(y_shard, y_ref[r0:r1])
 
+        # the overlap split: own-column part (needs only x_shard) + the rest (needs x_full)
+        from loops_b200.dist import split_columns
+        c0, c1 = row_range(cols, rank, world)
+        (o_off, o_idx, o_val), (r_off, r_idx, r_val) = split_columns(
+            torch.from_numpy(l_off), torch.from_numpy(np.ascontiguousarray(l_idx)),
+            torch.from_numpy(np.ascontiguousarray(l_val)), c0, c1)
+        assert int(o_off[-1]) + int(r_off[-1]) == len(l_idx)
+        assert o_idx.numel() == 0 or (int(o_idx.min()) >= 0 and int(o_idx.max()) < c1 - c0)
+        y_own = oracle.spmv(o_off.numpy(), o_idx.numpy(), o_val.numpy(), x_shard.numpy())
+        y_rest = oracle.spmv(r_off.numpy(), r_idx.numpy(), r_val.numpy(), x_full.numpy())
+        np.testing.assert_array_equal(y_own + y_rest, y_ref[r0:r1])      # exact inputs: any order of the adds
+
         # y shards concatenate to the global y (and are the next x shards)
         y_all = torch.empty(rows)
         dist.all_gather_into_tensor(y_all, torch.from_numpy(y_shard))
