@@ -304,6 +304,61 @@ int loopsb_emit_schedule(const loopsb_layout_t* lay, int schedule,
                          int32_t* dense_tile, int32_t* dense_atom,
                          int32_t* dense_emit, int64_t dense_len, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Format conversions on the device. The reference
+ * converts on the host and copies the result up (container/ell.hxx:113-145,
+ * bcsr.hxx:111-194, dia.hxx:135-188) or sorts zipped COO triples with thrust
+ * (coo.hxx:87-98, csr.hxx:86-94, csc.hxx:86-108, detail/convert.hxx:36-78).
+ * All pointers are DEVICE pointers; outputs are caller-allocated and bit-equal
+ * to the reference converters' for CSR input with unique columns per row. The
+ * calls use temporary device memory and synchronise the stream before
+ * returning (except loopsb_csr_to_ell, which is a single asynchronous launch).
+ * ------------------------------------------------------------------------- */
+/* row_indices[nnz]: the row of every atom (detail/convert.hxx:36-60). */
+int loopsb_csr_to_coo(int32_t num_rows, int64_t nnz, const int32_t* offsets,
+                      int32_t* row_indices, void* stream);
+/* Sort by (row, col) and compress the rows (csr.hxx:86-94); input order free. */
+int loopsb_coo_to_csr(int32_t num_rows, int64_t nnz, const int32_t* row_indices,
+                      const int32_t* col_indices, const float* values,
+                      int32_t* offsets /*[num_rows+1]*/, int32_t* indices /*[nnz]*/,
+                      float* out_values /*[nnz]*/, void* stream);
+/* Structural transpose, entries ordered by (column, row) (csc.hxx:86-108). */
+int loopsb_csr_to_csc(int32_t num_rows, int32_t num_cols, int64_t nnz,
+                      const int32_t* offsets, const int32_t* indices, const float* values,
+                      int32_t* csc_offsets /*[num_cols+1]*/, int32_t* csc_row_indices /*[nnz]*/,
+                      float* csc_values /*[nnz]*/, void* stream);
+/* ELL pitch = widest row (ell.hxx:121-126); *max_degree is a HOST int. */
+int loopsb_csr_max_degree(int32_t num_rows, const int32_t* offsets, int32_t* max_degree,
+                          void* stream);
+/* Row-major rows*pitch slabs, padding column -1 / value 0 (ell.hxx:128-140). */
+int loopsb_csr_to_ell(int32_t num_rows, int32_t pitch, const int32_t* offsets,
+                      const int32_t* indices, const float* values,
+                      int32_t* ell_indices /*[rows*pitch]*/, float* ell_values /*[rows*pitch]*/,
+                      void* stream);
+/* BCSR R x C (bcsr.hxx:111-194) in two calls. count: block_offsets[ceil(rows/R)+1],
+ * atom_block[nnz] = the block every atom lands in, *num_blocks (HOST). fill:
+ * block_col_indices[num_blocks] ascending per block-row, block_values
+ * [num_blocks*R*C] (fp32, or bf16 when bf16_values != 0), zero padding. */
+int loopsb_csr_to_bcsr_count(int32_t R, int32_t C, int32_t num_rows, int32_t num_cols, int64_t nnz,
+                             const int32_t* offsets, const int32_t* indices,
+                             int32_t* block_offsets, int32_t* atom_block, int64_t* num_blocks,
+                             void* stream);
+int loopsb_csr_to_bcsr_fill(int32_t R, int32_t C, int32_t num_rows, int32_t num_cols, int64_t nnz,
+                            const int32_t* offsets, const int32_t* indices, const float* values,
+                            const int32_t* atom_block, int64_t num_blocks,
+                            int32_t* block_col_indices, void* block_values, int32_t bf16_values,
+                            void* stream);
+/* DIA (dia.hxx:135-188) in two calls. count: *num_diagonals (HOST) = distinct
+ * (col - row). fill: diag_offsets[num_diagonals] ascending, dia_values
+ * [num_diagonals*rows] with values[d*rows + r], zero padding. */
+int loopsb_csr_to_dia_count(int32_t num_rows, int32_t num_cols, int64_t nnz,
+                            const int32_t* offsets, const int32_t* indices,
+                            int32_t* num_diagonals, void* stream);
+int loopsb_csr_to_dia_fill(int32_t num_rows, int32_t num_cols, int64_t nnz,
+                           const int32_t* offsets, const int32_t* indices, const float* values,
+                           int32_t num_diagonals, int32_t* diag_offsets, float* dia_values,
+                           void* stream);
+
 /* Grid the reference-compatible work_oriented launch uses on this device:
  * resident blocks per SM (occupancy API) x SM count, 128 threads per block
  * (algorithms/spmv/work_oriented.cuh:112-113). */

@@ -285,6 +285,24 @@ def _attach_from_tensors():
         self.num_blocks = int(block_col_indices.numel())
         return self
 
+    def csc_from_tensors(cls, rows, cols, offsets, indices, values):
+        self = cls.__new__(cls)
+        _planned.__init__(self)
+        self.rows, self.cols = int(rows), int(cols)
+        self.offsets, self.indices, self.values = offsets, indices, values
+        self.nnzs = int(indices.numel())
+        return self
+
+    def dia_from_tensors(cls, rows, cols, nnzs, diag_offsets, values):
+        self = cls.__new__(cls)
+        self.rows, self.cols, self.nnzs = int(rows), int(cols), int(nnzs)
+        self.stride = self.rows
+        self.diag_offsets, self.values = diag_offsets, values
+        self.num_diagonals = int(diag_offsets.numel())
+        return self
+
+    csc_t.from_tensors = classmethod(csc_from_tensors)
+    dia_t.from_tensors = classmethod(dia_from_tensors)
     coo_t.from_tensors = classmethod(coo_from_tensors)
     ell_t.from_tensors = classmethod(ell_from_tensors)
     bcsr_t.from_tensors = classmethod(bcsr_from_tensors)
@@ -294,26 +312,12 @@ _attach_from_tensors()
 
 
 def csr_to_coo_device(csr: "csr_t") -> "coo_t":
-    """CSR -> COO on the device (row ids by expanding the offsets)."""
-    deg = (csr.offsets[1:] - csr.offsets[:-1]).long()
-    rows_of = torch.repeat_interleave(torch.arange(csr.rows, device=csr.values.device, dtype=torch.int32), deg,
-                                      output_size=csr.nnzs)
-    return coo_t.from_tensors(csr.rows, csr.cols, rows_of, csr.indices, csr.values)
+    """CSR -> COO on the device (loops_b200.convert.csr_to_coo)."""
+    from .convert import csr_to_coo
+    return csr_to_coo(csr)
 
 
 def csr_to_ell_device(csr: "csr_t") -> "ell_t":
-    """CSR -> ELL on the device: pitch = widest row, padding column -1 / value 0
-    (same rules as the reference's host converter, ell.hxx:113-145)."""
-    dev = csr.values.device
-    off = csr.offsets.long()
-    deg = off[1:] - off[:-1]
-    pitch = int(deg.max().item()) if csr.rows else 0
-    e_idx = torch.full((csr.rows * pitch,), -1, dtype=torch.int32, device=dev)
-    e_val = torch.zeros(csr.rows * pitch, dtype=torch.float32, device=dev)
-    if csr.nnzs:
-        row_of = torch.repeat_interleave(torch.arange(csr.rows, device=dev), deg, output_size=csr.nnzs)
-        slot = torch.arange(csr.nnzs, device=dev) - off[row_of]
-        dst = row_of * pitch + slot
-        e_idx[dst] = csr.indices
-        e_val[dst] = csr.values
-    return ell_t.from_tensors(csr.rows, csr.cols, csr.nnzs, pitch, e_idx, e_val)
+    """CSR -> ELL on the device (loops_b200.convert.csr_to_ell)."""
+    from .convert import csr_to_ell
+    return csr_to_ell(csr)

@@ -623,8 +623,13 @@ __device__ __noinline__ void cold_update(float* ys, int r0, int r1, int r2, int 
   ys[a3] = y3 + v3;
 }
 
+#ifndef LOOPSB_STAMPS_ONLY
+#define LOOPSB_STAMPS_ONLY 0   // 1: PROFILE builds keep only wall-clock stamps (no per-step cycle counters)
+#endif
 template <int WARPS, int DEPTH, bool PROFILE = false>
 __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const params p) {
+  constexpr bool COUNT = PROFILE && !LOOPSB_STAMPS_ONLY;   // per-step cycle counters (slow the loop ~2x)
+  constexpr bool STAMP = PROFILE && LOOPSB_STAMPS_ONLY;    // per-warp wall-clock stamps only
   extern __shared__ __align__(16) unsigned char bt_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x;
@@ -648,10 +653,49 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
   const int ys_words = (p.rb + 1 + 3) & ~3;
   int* last_flag = reinterpret_cast<int*>(ys + ys_words);
 
+  // The kernel is one wave of CTAs that all start together, so whatever precedes the
+  // first stream data is time HBM sits idle. Order of the prologue: the producer
+  // thread arms the ring and requests the first xb bands; every consumer warp requests
+  // the first DEPTH steps of its stream (registers) and the steps behind them (L2);
+  // only then is the y tile zeroed, under those loads.
+  const uint64_t keep = loops::tma::policy_evict_last();
+  const int col0 = qi * p.cq;
+  const int part_cols = min(p.cq, p.cols - col0);
+  auto request_band = [&](int b, int k) {   // producer thread only
+    const int c0 = b * p.cb;
+    int n = min(p.cb, part_cols - c0);
+    if (n < 0) n = 0;
+    const int n16 = n & ~3;
+    float* dst = xs + k * p.cb;
+    const float* src = p.x + col0 + c0;
+    for (int t = n16; t < n; ++t) dst[t] = src[t];  // ragged tail of the last band
+    if (n16 > 0) {
+      loops::tma::barrier_arrive_expect_tx(&xfull[k], uint32_t(n16) * 4u);
+      loops::tma::bulk_g2s_hint(dst, src, uint32_t(n16) * 4u, &xfull[k], keep);
+    } else {
+      loops::tma::barrier_arrive(&xfull[k]);
+    }
+  };
   if (boss) {
     for (int k = 0; k < p.xb; ++k) {
       loops::tma::barrier_init(&xfull[k], 1);
       loops::tma::barrier_init(&xempty[k], WARPS);
+    }
+    for (int b = 0; b < min(p.xb, p.nband); ++b) request_band(b, b);
+  }
+  const bool consumer = warp < WARPS;
+  const int ws = consumer ? cta * WARPS + warp : 0;
+  const int sbase = p.stream_base[ws];
+  const int nsteps = consumer ? p.stream_base[ws + 1] - sbase : 0;
+  const uint32_t* src = p.steps + size_t(sbase) * kStepWords;
+  step_regs buf[DEPTH];
+  if (consumer) {
+#pragma unroll
+    for (int k = 0; k < DEPTH; ++k) load_step(buf[k], src + size_t(k) * kStepWords, lane);
+    // steps DEPTH .. DEPTH + l2_ahead - 1: 128-byte lines, four steps per pass of the warp
+    for (int t = 0; t < p.l2_ahead; t += 4) {
+      const uint32_t* far = src + size_t(DEPTH + t) * kStepWords + lane * 32;
+      if (lane < 8 * (p.l2_ahead - t) && far < p.steps_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(far));
     }
   }
   for (int i = tid; i < ys_words; i += (WARPS + 1) * 32) ys[i] = 0.f;
@@ -660,41 +704,19 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
   if (PROFILE && stamps && boss) stamps[1] = wall_ns();
 
   if (warp == WARPS) {
-    // ---- x producer: one thread walks the bands of this column part ----
+    // ---- x producer: one thread walks the remaining bands of this column part ----
     if (lane == 0) {
-      const uint64_t keep = loops::tma::policy_evict_last();
-      const int col0 = qi * p.cq;
-      const int part_cols = min(p.cq, p.cols - col0);
       int k = 0;
-      uint32_t par = 1;  // parity of the PREVIOUS use of slot k (first pass: nothing to wait for)
-      for (int b = 0; b < p.nband; ++b) {
-        if (b >= p.xb) loops::tma::barrier_wait_suspend(&xempty[k], par);
-        const int c0 = b * p.cb;
-        int n = min(p.cb, part_cols - c0);
-        if (n < 0) n = 0;
-        const int n16 = n & ~3;
-        float* dst = xs + k * p.cb;
-        const float* src = p.x + col0 + c0;
-        for (int t = n16; t < n; ++t) dst[t] = src[t];  // ragged tail of the last band
-        if (n16 > 0) {
-          loops::tma::barrier_arrive_expect_tx(&xfull[k], uint32_t(n16) * 4u);
-          loops::tma::bulk_g2s_hint(dst, src, uint32_t(n16) * 4u, &xfull[k], keep);
-        } else {
-          loops::tma::barrier_arrive(&xfull[k]);
-        }
+      uint32_t par = 0;  // parity of the PREVIOUS use of slot k
+      for (int b = p.xb; b < p.nband; ++b) {
+        loops::tma::barrier_wait_suspend(&xempty[k], par);
+        request_band(b, k);
         if (++k == p.xb) { k = 0; par ^= 1u; }
       }
     }
   } else {
     // ---- consumer warp: its own stream, its own rows ----
     __syncwarp();
-    const int ws = cta * WARPS + warp;
-    const int sbase = p.stream_base[ws];
-    const int nsteps = p.stream_base[ws + 1] - sbase;
-    const uint32_t* src = p.steps + size_t(sbase) * kStepWords;
-    step_regs buf[DEPTH];
-#pragma unroll
-    for (int k = 0; k < DEPTH; ++k) load_step(buf[k], src + size_t(k) * kStepWords, lane);
     const uint32_t* refill = src + size_t(DEPTH) * kStepWords;  // next step to request
     const size_t l2_ahead_words = size_t(p.l2_ahead) * kStepWords;
     const uint32_t* l2_end = p.l2_guard ? src + size_t(nsteps) * kStepWords : p.steps_end;   // A/B: stop the L2 prefetch at the stream's end
@@ -733,8 +755,9 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
         --nheld;
       }
     };
+    long long w_first = 0;
     long long t_stream = 0, t_band = 0, t_gather = 0, t_rmw = 0, n_slow = 0, t0 = 0;
-    const long long t_begin = PROFILE ? clock64() : 0;
+    const long long t_begin = COUNT ? clock64() : 0;
     const int scratch = p.rb;
     // (Issuing the x gathers of step s+1 ahead of the y updates of step s was
     // tried and measured slower: a warp that then blocks on the x ring sits on
@@ -749,11 +772,12 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
         // moves that wait on the load just issued -- a synchronous "prefetch")
         const uint4 I = buf[k].I;
         const float4 V = buf[k].V;
-        if (PROFILE) t0 = clock64();
+        if (COUNT) t0 = clock64();
         const uint32_t m = __ballot_sync(0xffffffffu, (I.x & kFlagBit) != 0u);   // the step's control word
-        if (PROFILE) { const long long t1 = clock64(); t_stream += t1 - t0; t0 = t1; }
+        if (STAMP && s0 == 0 && k == 0) w_first = wall_ns();
+        if (COUNT) { const long long t1 = clock64(); t_stream += t1 - t0; t0 = t1; }
         if (m >> kMetaLeadShift) band_events(m);
-        if (PROFILE) { const long long t1 = clock64(); t_band += t1 - t0; t0 = t1; }
+        if (COUNT) { const long long t1 = clock64(); t_band += t1 - t0; t0 = t1; }
         const float p0 = __fmul_rn(V.x, xs[I.x & 0xffffu]);
         const float p1 = __fmul_rn(V.y, xs[I.y & 0xffffu]);
         const float p2 = __fmul_rn(V.z, xs[I.z & 0xffffu]);
@@ -761,7 +785,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
         const int r0 = int((I.x >> 16) & 0x7fffu), r1 = int((I.y >> 16) & 0x7fffu);
         const int r2 = int((I.z >> 16) & 0x7fffu), r3 = int((I.w >> 16) & 0x7fffu);
         const bool dirty = (m & (1u | kMetaLongBit)) != 0u;   // anything but the one-hand-off fast path
-        if (PROFILE) { const long long t1 = clock64(); t_gather += (p0 + p1 + p2 + p3 == 12345.f) ? 1 : t1 - t0; t0 = t1; }
+        if (COUNT) { const long long t1 = clock64(); t_gather += (p0 + p1 + p2 + p3 == 12345.f) ? 1 : t1 - t0; t0 = t1; }
         if (!dirty) {
           // Every row of the step is one contiguous range of cells. Sum runs inside the
           // lane, hand the part of a run that lies in later lanes back to the lane where
@@ -792,9 +816,9 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
           ys[a3] = y3 + v3;
         } else {
           cold_update(ys, r0, r1, r2, r3, p0, p1, p2, p3, scratch, (m & 1u) != 0u);
-          if (PROFILE) ++n_slow;
+          if (COUNT) ++n_slow;
         }
-        if (PROFILE) t_rmw += clock64() - t0;
+        if (COUNT) t_rmw += clock64() - t0;
         __syncwarp();   // y rows of this step are settled before the next step's loads
         release(int(m >> kMetaRelShift) & 0xf);
         // step s + DEPTH into the registers just freed, and step s + DEPTH + kL2Ahead
@@ -819,7 +843,11 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
       if (lane == 0) loops::tma::barrier_arrive(&xempty[acq_k]);
       advance();
     }
-    if (PROFILE && lane == 0 && p.prof) {
+    if (STAMP && lane == 0 && p.prof) {
+      long long* o = p.prof + size_t(ws) * 8;
+      o[0] = w_first; o[1] = wall_ns(); o[7] = nsteps;
+    }
+    if (COUNT && lane == 0 && p.prof) {
       long long* o = p.prof + size_t(ws) * 8;
       o[0] = t_stream; o[1] = t_band; o[2] = t_gather; o[3] = t_rmw; o[4] = 0; o[5] = n_slow;
       o[6] = clock64() - t_begin; o[7] = nsteps;
@@ -847,30 +875,43 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
   const int n4 = (rows_here + 3) >> 2;
   float4* mine = reinterpret_cast<float4*>(p.partial + size_t(qi) * pitch + size_t(rbi) * rb4);
   const float4* ys4 = reinterpret_cast<const float4*>(ys);
-  for (int i = tid; i < n4; i += NT) __stcg(mine + i, ys4[i]);
-  __threadfence();
-  __syncthreads();
   int lo = 0, hi = n4;
-  if (p.peers) {
-    if (tid == 0) {
-      atomicAdd(&p.counters[rbi], 1u);
-      volatile unsigned* c = p.counters + rbi;
-      while (*c < unsigned(p.q)) __nanosleep(64);
-    }
-    __syncthreads();
+  if (p.peers) {   // the rows this CTA reduces itself never leave its shared memory
     const int chunk = (n4 + p.q - 1) / p.q;
     lo = min(n4, qi * chunk);
     hi = min(n4, lo + chunk);
+    for (int i = tid; i < n4 - (hi - lo); i += NT) {
+      const int j = i < lo ? i : i + (hi - lo);
+      __stcg(mine + j, ys4[j]);
+    }
+  } else {
+    for (int i = tid; i < n4; i += NT) __stcg(mine + i, ys4[i]);
+  }
+  // release: the CTA's stores are ordered before thread 0's fence by the barrier, and
+  // the fence (cumulative, device scope) orders them before the counter update
+  __syncthreads();
+  if (STAMP && tid == 0 && p.prof) p.prof[size_t(cta) * WARPS * 8 + 3] = wall_ns();   // partial rows stored
+  if (p.peers) {
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(&p.counters[rbi], 1u);
+      volatile unsigned* c = p.counters + rbi;
+      while (*c < unsigned(p.q)) __nanosleep(32);
+      __threadfence();   // acquire: the peers' partials are read after the count was seen
+      if (STAMP && p.prof) p.prof[size_t(cta) * WARPS * 8 + 2] = wall_ns();             // all q partials visible
+    }
+    __syncthreads();
   } else {
     if (tid == 0) {
+      __threadfence();
       const unsigned t = atomicAdd(&p.counters[rbi], 1u);
       *last_flag = (t == unsigned(p.q - 1));
+      __threadfence();
     }
     __syncthreads();
     if (!*last_flag) hi = 0;
   }
   if (hi > lo) {
-    __threadfence();
     const float4* part = reinterpret_cast<const float4*>(p.partial + size_t(rbi) * rb4);
     const size_t pitch4 = pitch >> 2;
     // three row groups per thread and trip, all their partial loads issued

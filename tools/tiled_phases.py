@@ -28,6 +28,16 @@ for geo in sys.argv[1:] or ["0,0,0,0,0,0"]:
     t0 = st[:, 0].min()
     print(f"   wall clock (us from first CTA entry): entry max {(st[:,0].max()-t0)/1e3:.1f}; init done mean {(st[:,1]-t0).mean()/1e3:.1f} max {(st[:,1]-t0).max()/1e3:.1f}; "
           f"loop done mean {(st[:,2]-t0).mean()/1e3:.1f} min {(st[:,2]-t0).min()/1e3:.1f} max {(st[:,2]-t0).max()/1e3:.1f}; CTA end mean {(st[:,3]-t0).mean()/1e3:.1f} max {(st[:,3]-t0).max()/1e3:.1f}")
+    if os.environ.get("STAMPS_ONLY"):   # library built with -DLOOPSB_STAMPS_ONLY=1: wall-clock stamps only
+        W = info["warps"]; o = out.astype(float)
+        first, wend = o[:, 0] - t0, o[:, 1] - t0
+        pub, vis = o[::W, 3] - t0, o[::W, 2] - t0
+        print(f"{geo}: launch {e0.elapsed_time(e1)*1e3:.1f} us; per warp: first step ready mean {first.mean()/1e3:.2f} max {first.max()/1e3:.2f}; "
+              f"stream done mean {wend.mean()/1e3:.2f} min {wend.min()/1e3:.2f} max {wend.max()/1e3:.2f}")
+        print(f"   per CTA: partials stored mean {pub.mean()/1e3:.2f} max {pub.max()/1e3:.2f}; peers visible mean {vis.mean()/1e3:.2f} max {vis.max()/1e3:.2f}; "
+              f"end mean {(st[:,3]-t0).mean()/1e3:.2f} max {(st[:,3]-t0).max()/1e3:.2f}", flush=True)
+        A.drop_plans()
+        continue
     steps = out[:, 7].astype(float); m = steps > 0
     print(f"{geo}: launch {e0.elapsed_time(e1)*1e3:.1f} us (profiled build); warps {ns}, steps/warp {steps[m].mean():.1f}, "
           f"warp total cycles mean {out[m,6].mean():.0f} max {out[:,6].max()}")
