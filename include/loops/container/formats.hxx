@@ -2,8 +2,11 @@
  * @file formats.hxx
  * @brief Sparse containers. Same struct names, members, dtypes and padding
  * rules as the reference (include/loops/container/{csr,coo,ell,bcsr}.hxx);
- * they are the INPUT MEMORY FORMATS of the SpMV path. Conversions run on the
- * host with std:: algorithms (set-up code, not the hot path).
+ * they are the INPUT MEMORY FORMATS of the SpMV path. Conversions between two
+ * DEVICE containers of (int, int, float) run on the device through the C ABI
+ * (loopsb_csr_to_* / loopsb_coo_to_csr, csrc/convert.cu -- the reference does
+ * these with host loops); every other combination runs on the
+ * host with std:: algorithms, with the same results.
  */
 #pragma once
 
@@ -12,12 +15,28 @@
 #include <numeric>
 #include <vector>
 
+#include <type_traits>
+
 #include <loops/container/vector.hxx>
 #include <loops/container/layout.hxx>
+#include <loops/error.hxx>
 #include <loops/memory.hxx>
+#include <loopsb.h>
 
 namespace loops {
 using namespace memory;
+
+namespace detail {
+/// Both sides on the device with the C ABI's types: convert on the device.
+template <typename index_t, typename offset_t, typename value_t, memory_space_t a, memory_space_t b>
+inline constexpr bool device_conversion_v =
+    a == memory_space_t::device && b == memory_space_t::device && std::is_same_v<index_t, int> &&
+    std::is_same_v<offset_t, int> && std::is_same_v<value_t, float>;
+template <typename vec_t>
+auto* raw(vec_t& v) { return thrust::raw_pointer_cast(v.data()); }
+template <typename vec_t>
+const auto* raw(const vec_t& v) { return thrust::raw_pointer_cast(v.data()); }
+}  // namespace detail
 
 template <typename index_t, typename value_t, memory_space_t space = memory_space_t::device>
 struct coo_t;
@@ -84,6 +103,15 @@ struct csr_t {
   template <auto rhs_space>
   csr_t(const coo_t<index_t, value_t, rhs_space>& coo)
       : rows(coo.rows), cols(coo.cols), nnzs(coo.nnzs) {
+    if constexpr (detail::device_conversion_v<index_t, offset_t, value_t, space, rhs_space>) {
+      offsets.resize(rows + 1); indices.resize(nnzs); values.resize(nnzs);
+      error::throw_if_status(
+          loopsb_coo_to_csr(int(rows), int64_t(nnzs), detail::raw(coo.row_indices), detail::raw(coo.col_indices),
+                            detail::raw(coo.values), detail::raw(offsets), detail::raw(indices), detail::raw(values),
+                            nullptr),
+          "loopsb_coo_to_csr");
+      return;
+    }
     coo_t<index_t, value_t, memory_space_t::host> sorted(coo);
     sorted.sort_by_row();
     thrust::host_vector<offset_t> off(rows + 1, offset_t(0));
@@ -107,6 +135,13 @@ template <typename index_t, typename value_t, memory_space_t space>
 template <auto rhs_space, typename offset_t>
 coo_t<index_t, value_t, space>::coo_t(const csr_t<index_t, offset_t, value_t, rhs_space>& csr)
     : rows(csr.rows), cols(csr.cols), nnzs(csr.nnzs), col_indices(csr.indices), values(csr.values) {
+  if constexpr (detail::device_conversion_v<index_t, offset_t, value_t, space, rhs_space>) {
+    row_indices.resize(nnzs);
+    error::throw_if_status(
+        loopsb_csr_to_coo(int(rows), int64_t(nnzs), detail::raw(csr.offsets), detail::raw(row_indices), nullptr),
+        "loopsb_csr_to_coo");
+    return;
+  }
   thrust::host_vector<offset_t> off(csr.offsets);
   thrust::host_vector<index_t> r(nnzs);
   for (std::size_t row = 0; row < rows; ++row)
@@ -135,6 +170,12 @@ struct ell_t {
 
   template <typename offset_t, auto rhs_space>
   static std::size_t max_nnz_per_row(const csr_t<index_t, offset_t, value_t, rhs_space>& csr) {
+    if constexpr (detail::device_conversion_v<index_t, offset_t, value_t, rhs_space, rhs_space>) {
+      int widest = 0;
+      error::throw_if_status(loopsb_csr_max_degree(int(csr.rows), detail::raw(csr.offsets), &widest, nullptr),
+                             "loopsb_csr_max_degree");
+      return std::size_t(widest);
+    }
     thrust::host_vector<offset_t> off(csr.offsets);
     std::size_t widest = 0;
     for (std::size_t r = 0; r < csr.rows; ++r)
@@ -146,6 +187,15 @@ struct ell_t {
   template <typename offset_t, auto rhs_space>
   ell_t(const csr_t<index_t, offset_t, value_t, rhs_space>& csr)
       : rows(csr.rows), cols(csr.cols), nnzs(csr.nnzs), pitch(max_nnz_per_row(csr)) {
+    if constexpr (detail::device_conversion_v<index_t, offset_t, value_t, space, rhs_space>) {
+      indices.resize(rows * pitch); values.resize(rows * pitch);
+      error::throw_if_status(
+          loopsb_csr_to_ell(int(rows), int(pitch), detail::raw(csr.offsets), detail::raw(csr.indices),
+                            detail::raw(csr.values), detail::raw(indices), detail::raw(values), nullptr),
+          "loopsb_csr_to_ell");
+      error::throw_if_exception(cudaStreamSynchronize(nullptr) != cudaSuccess, "csr -> ell failed on the device");
+      return;
+    }
     thrust::host_vector<offset_t> off(csr.offsets);
     thrust::host_vector<index_t> idx(csr.indices);
     thrust::host_vector<value_t> val(csr.values);
@@ -193,6 +243,25 @@ struct bcsr_t {
   bcsr_t(const csr_t<index_t, csr_offset_t, value_t, rhs_space>& csr)
       : rows(csr.rows), cols(csr.cols), nnzs(csr.nnzs),
         num_block_rows((csr.rows + R - 1) / R), num_block_cols((csr.cols + C - 1) / C) {
+    if constexpr (detail::device_conversion_v<index_t, csr_offset_t, value_t, space, rhs_space> &&
+                  std::is_same_v<offset_t, int>) {
+      block_offsets.resize(num_block_rows + 1);
+      vector_t<int, memory_space_t::device> atom_block(nnzs);
+      int64_t nb = 0;
+      error::throw_if_status(
+          loopsb_csr_to_bcsr_count(int(R), int(C), int(rows), int(cols), int64_t(nnzs), detail::raw(csr.offsets),
+                                   detail::raw(csr.indices), detail::raw(block_offsets), detail::raw(atom_block), &nb,
+                                   nullptr),
+          "loopsb_csr_to_bcsr_count");
+      num_blocks = std::size_t(nb);
+      block_col_indices.resize(num_blocks); values.resize(num_blocks * kBlockSize);
+      error::throw_if_status(
+          loopsb_csr_to_bcsr_fill(int(R), int(C), int(rows), int(cols), int64_t(nnzs), detail::raw(csr.offsets),
+                                  detail::raw(csr.indices), detail::raw(csr.values), detail::raw(atom_block), nb,
+                                  detail::raw(block_col_indices), detail::raw(values), 0, nullptr),
+          "loopsb_csr_to_bcsr_fill");
+      return;
+    }
     thrust::host_vector<csr_offset_t> off(csr.offsets);
     thrust::host_vector<index_t> idx(csr.indices);
     thrust::host_vector<value_t> val(csr.values);
@@ -253,6 +322,15 @@ struct csc_t {
   template <auto rhs_space>
   csc_t(const csr_t<index_t, offset_t, value_t, rhs_space>& csr)
       : rows(csr.rows), cols(csr.cols), nnzs(csr.nnzs) {
+    if constexpr (detail::device_conversion_v<index_t, offset_t, value_t, space, rhs_space>) {
+      offsets.resize(cols + 1); indices.resize(nnzs); values.resize(nnzs);
+      error::throw_if_status(
+          loopsb_csr_to_csc(int(rows), int(cols), int64_t(nnzs), detail::raw(csr.offsets), detail::raw(csr.indices),
+                            detail::raw(csr.values), detail::raw(offsets), detail::raw(indices), detail::raw(values),
+                            nullptr),
+          "loopsb_csr_to_csc");
+      return;
+    }
     thrust::host_vector<offset_t> off(csr.offsets);
     thrust::host_vector<index_t> idx(csr.indices);
     thrust::host_vector<value_t> val(csr.values);
@@ -302,6 +380,21 @@ struct dia_t {
   template <auto rhs_space, typename csr_offset_t>
   dia_t(const csr_t<index_t, csr_offset_t, value_t, rhs_space>& csr)
       : rows(csr.rows), cols(csr.cols), nnzs(csr.nnzs), stride(csr.rows) {
+    if constexpr (detail::device_conversion_v<index_t, csr_offset_t, value_t, space, rhs_space>) {
+      int nd = 0;
+      error::throw_if_status(
+          loopsb_csr_to_dia_count(int(rows), int(cols), int64_t(nnzs), detail::raw(csr.offsets),
+                                  detail::raw(csr.indices), &nd, nullptr),
+          "loopsb_csr_to_dia_count");
+      num_diagonals = std::size_t(nd);
+      diag_offsets.resize(num_diagonals); values.resize(num_diagonals * stride);
+      error::throw_if_status(
+          loopsb_csr_to_dia_fill(int(rows), int(cols), int64_t(nnzs), detail::raw(csr.offsets),
+                                 detail::raw(csr.indices), detail::raw(csr.values), nd, detail::raw(diag_offsets),
+                                 detail::raw(values), nullptr),
+          "loopsb_csr_to_dia_fill");
+      return;
+    }
     const std::vector<index_t> offs = sorted_offsets(csr);
     num_diagonals = offs.size();
     thrust::host_vector<csr_offset_t> off(csr.offsets);

@@ -209,6 +209,29 @@ int main() {
     vector_t<float> xp(bcsr.num_block_cols * 4, 0.0f);
     thrust::copy(x.begin(), x.end(), xp.begin());
     algorithms::spmv::bcsr_thread_mapped(bcsr, xp, y); check("algorithms::spmv::bcsr_thread_mapped<4,4>", y, ref);
+    // device-space constructors convert on the device (csrc/convert.cu); host-space
+    // ones run the host loops: the arrays must be identical
+    {
+      auto same = [](const auto& dv, const auto& hv) {
+        thrust::host_vector<typename std::decay_t<decltype(hv)>::value_type> back(dv);
+        return back.size() == hv.size() && std::equal(back.begin(), back.end(), hv.begin());
+      };
+      coo_t<int, float, memory_space_t::host> coo_h(h);
+      ell_t<int, float, memory_space_t::host> ell_h(h);
+      bcsr_t<4, 4, int, int, float, memory_space_t::host> bcsr_h(h);
+      csc_t<int, int, float, memory_space_t::host> csc_h(h);
+      csc_t<int, int, float> csc_d(csr);
+      csr_t<int, int, float> back_d(coo);            // coo -> csr on the device
+      bool ok = same(coo.row_indices, coo_h.row_indices) && ell.pitch == ell_h.pitch &&
+                same(ell.indices, ell_h.indices) && same(ell.values, ell_h.values) &&
+                bcsr.num_blocks == bcsr_h.num_blocks && same(bcsr.block_offsets, bcsr_h.block_offsets) &&
+                same(bcsr.block_col_indices, bcsr_h.block_col_indices) && same(bcsr.values, bcsr_h.values) &&
+                same(csc_d.offsets, csc_h.offsets) && same(csc_d.indices, csc_h.indices) &&
+                same(csc_d.values, csc_h.values) && same(back_d.offsets, h.offsets) &&
+                same(back_d.indices, h.indices) && same(back_d.values, h.values);
+      if (!ok) ++failures;
+      std::printf("%s device conversions == host conversions (coo, ell, bcsr<4,4>, csc, coo->csr)\n", ok ? "OK" : "FAIL");
+    }
   } catch (const error::exception_t& e) {
     std::printf("FAIL exception: %s\n", e.what());
     return 100;
