@@ -87,7 +87,12 @@ def coo_to_csr(rows, cols, r, c, v):
 
 def load_csr(path: str, device="cuda"):
     """Matrix Market file -> ``csr_t`` on ``device`` (examples/spmv/helpers.hxx flow)."""
-    from .container import csr_t
+    from .container import coo_t, csr_t
     rows, cols, r, c, v = load_coo(path)
+    if str(device).startswith("cuda"):
+        # the triples go up in file order; sorting and row compression run on the
+        # device (loopsb_coo_to_csr: stable radix sort by (row, col), duplicates kept)
+        from .convert import coo_to_csr as coo_to_csr_device
+        return coo_to_csr_device(coo_t(rows, cols, r, c, v, device=device))
     off, idx, val = coo_to_csr(rows, cols, r, c, v)
     return csr_t(rows, cols, off, idx, val, device=device)

@@ -205,3 +205,20 @@ def test_full_size_config2_round_trips():
     assert abs(float(B.values.double().sum().item()) - float(val.double().sum().item())) < 1e-3
     per_block = B.values.view(-1, 16).ne(0).sum(1)
     assert int(per_block.min().item()) >= 1 and int(per_block.sum().item()) == 1 << 25
+
+
+def test_market_file_to_device_csr(tmp_path):
+    """Matrix Market file -> device CSR with the sort and row compression on the
+    device equals the host path (symmetric mirrors, a duplicate entry kept in file
+    order, empty rows; reference container/market.hxx:100-289 + csr.hxx:86-94)."""
+    from loops_b200 import market
+    path = tmp_path / "m.mtx"
+    path.write_text("%%MatrixMarket matrix coordinate real symmetric\n% comment\n6 6 7\n"
+                    "3 1 2.5\n1 1 1.0\n5 2 -3.0\n6 5 4.0\n3 1 7.0\n2 2 0.5\n6 1 9.0\n")
+    R, Cc, r, c, v = market.load_coo(str(path))
+    off, idx, val = market.coo_to_csr(R, Cc, r, c, v)
+    A = market.load_csr(str(path), device="cuda")
+    assert (A.rows, A.cols, A.nnzs) == (6, 6, len(idx))
+    assert np.array_equal(_np(A.offsets), off)
+    assert np.array_equal(_np(A.indices), idx)
+    assert np.array_equal(_np(A.values), val)
