@@ -512,16 +512,23 @@ def main():
 
     e2e_pipelined(2 * NBUF)
     torch.cuda.synchronize()
-    e2e_s = timed(lambda: e2e_pipelined(args.steps))
+    # wall-clock over K steps is sensitive to what else the host and the PCIe link are
+    # doing; the loop is repeated three times and the MEDIAN repetition is reported
+    e2e_reps = []
+    for _ in range(3):
+        e2e_reps.append(timed(lambda: e2e_pipelined(args.steps)))
+        torch.cuda.synchronize()
+    e2e_s = sorted(e2e_reps)[1]
     e2e = {"value": nnz / (e2e_s / args.steps), "unit": UNIT,
            "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(y_host[0].numel() * 4),
            "ms_per_step": e2e_s / args.steps * 1e3,
+           "ms_per_step_repetitions": [t / args.steps * 1e3 for t in e2e_reps],
            "serial_value": nnz / (serial_s / args.steps), "serial_ms_per_step": serial_s / args.steps * 1e3,
            "note": "matrix resident in HBM (the reference API's csr_t is device-resident); every step uploads "
                    "x from pinned host memory and downloads y; `value` overlaps the copies of neighbouring "
                    "steps on side streams (4 buffers in flight; at N=1 issued through the CUDA runtime and the "
                    "C ABI directly, as a C caller would), `serial_value` runs copy-in/SpMV/copy-out back to "
-                   "back; wall clock, final synchronize on all streams"}
+                   "back; wall clock, final synchronize on all streams; median of three repetitions of the K-step loop"}
     y_e2e_ok = bool(torch.equal(torch.from_numpy(y_host[(args.steps - 1) % NBUF].numpy()).to(dev), yd[(args.steps - 1) % NBUF]))
 
     # correctness guard on the timed configuration (exact inputs -> exact sums)
