@@ -207,6 +207,26 @@ util::timer_t bcsr_thread_mapped(bcsr_t<R, C, int, int, float>& bcsr, vector_t<f
   return timer;
 }
 
+/// The schedule the library would pick for this matrix (the
+/// reference publishes its heuristic's outcomes in plots/data/heuristics.csv).
+/// The widest row is computed on the device.
+inline schedule::algorithms_t select_schedule(csr_t<int, int, float>& csr) {
+  int widest = -1, pick = LOOPSB_SCHED_MERGE_PATH_FLAT;
+  if (csr.rows > 0)
+    error::throw_if_status(loopsb_csr_max_degree(int32_t(csr.rows), detail::raw(csr.offsets), &widest, nullptr),
+                           "loopsb_csr_max_degree");
+  error::throw_if_status(loopsb_select_schedule(int32_t(csr.rows), int32_t(csr.cols), int64_t(csr.nnzs), widest, &pick),
+                         "loopsb_select_schedule");
+  return pick == LOOPSB_SCHED_THREAD_MAPPED ? schedule::algorithms_t::thread_mapped
+                                            : schedule::algorithms_t::merge_path_flat;
+}
+
+/// SpMV through the schedule select_schedule() picks.
+inline void automatic(csr_t<int, int, float>& csr, vector_t<float>& x, vector_t<float>& y, cudaStream_t stream = 0) {
+  if (select_schedule(csr) == schedule::algorithms_t::thread_mapped) thread_mapped(csr, x, y, stream);
+  else merge_path_flat(csr, x, y, stream);
+}
+
 }  // namespace spmv
 }  // namespace algorithms
 }  // namespace loops

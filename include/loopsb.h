@@ -359,6 +359,14 @@ int loopsb_csr_to_dia_fill(int32_t num_rows, int32_t num_cols, int64_t nnz,
                            int32_t num_diagonals, int32_t* diag_offsets, float* dia_values,
                            void* stream);
 
+/* Which schedule to run for a CSR matrix (the
+ * reference publishes the outcome of its heuristic per matrix in
+ * plots/data/heuristics.csv). max_degree < 0 = unknown (then only nnz decides,
+ * like the reference's rule); loopsb_csr_max_degree computes it on the device.
+ * Pure host function: no device is touched. */
+int loopsb_select_schedule(int32_t num_rows, int32_t num_cols, int64_t nnz,
+                           int32_t max_degree, int32_t* schedule);
+
 /* Grid the reference-compatible work_oriented launch uses on this device:
  * resident blocks per SM (occupancy API) x SM count, 128 threads per block
  * (algorithms/spmv/work_oriented.cuh:112-113). */

@@ -199,3 +199,28 @@ BY_NAME = {
     "thread_mapped": thread_mapped,
     "group_mapped": group_mapped,
 }
+
+
+def select_schedule(csr: csr_t, max_degree: int | None = None) -> str:
+    """Name of the schedule ``loopsb_select_schedule`` picks for this matrix
+    (thresholds measured by tools/heuristic_sweep.py). ``max_degree``
+    None = compute it on the device when the matrix is there, else leave it unknown."""
+    import ctypes as C
+    if max_degree is None:
+        if csr.values.is_cuda and csr.rows:
+            from ..convert import csr_max_degree
+            max_degree = csr_max_degree(csr)
+        else:
+            max_degree = -1
+    out = C.c_int32(0)
+    _lib.check(_lib.load().loopsb_select_schedule(csr.rows, csr.cols, csr.nnzs, int(max_degree), C.byref(out)),
+               "loopsb_select_schedule")
+    return {v: k for k, v in _lib.SCHEDULE_NAMES.items()}[int(out.value)]
+
+
+def automatic(csr: csr_t, x, y, stream=None, sync=True):
+    """SpMV with the schedule ``select_schedule`` picks (the choice is cached on the container)."""
+    name = getattr(csr, "_auto_schedule", None)
+    if name is None:
+        name = csr._auto_schedule = select_schedule(csr)
+    return BY_NAME[name](csr, x, y, stream=stream, sync=sync)

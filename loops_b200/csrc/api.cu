@@ -541,6 +541,29 @@ int loopsb_work_oriented_grid(int32_t* grid_blocks) {
   return LOOPSB_OK;
 }
 
+// Schedule selection. The reference's paper picks thread-mapped /
+// group-mapped / merge-path from the matrix sizes (plots/data/heuristics.csv: its
+// `kernel` column is merge-path exactly when nnz >= 10,000 on all but 4 of 4831
+// matrices). Thresholds here are from tools/heuristic_sweep.py on B200
+// (profiles/heuristic_sweep_r01.log): below ~10^4 nonzeros every kernel is one
+// launch latency and thread_mapped is the cheapest launch; very light rows
+// (average degree <= 4) also favour thread_mapped, but only when no row is heavy
+// (one lane walks a row); everything else goes to merge_path_flat, whose plan
+// additionally takes the band-tiled path when its cost model accepts the matrix.
+int loopsb_select_schedule(int32_t num_rows, int32_t num_cols, int64_t nnz, int32_t max_degree,
+                           int32_t* schedule) {
+  LOOPSB_REQUIRE(schedule != nullptr, "schedule is null");
+  LOOPSB_REQUIRE(num_rows >= 0 && num_cols >= 0 && nnz >= 0, "negative dimensions");
+  int pick = LOOPSB_SCHED_MERGE_PATH_FLAT;
+  if (nnz < 10000) {
+    pick = LOOPSB_SCHED_THREAD_MAPPED;
+  } else if (max_degree >= 0 && max_degree <= 32 && nnz <= 4 * int64_t(num_rows)) {
+    pick = LOOPSB_SCHED_THREAD_MAPPED;
+  }
+  *schedule = pick;
+  return LOOPSB_OK;
+}
+
 int loopsb_plan_destroy(loopsb_plan_t* plan) {
   if (!plan) return LOOPSB_OK;
   if (plan->coords) cudaFree(plan->coords);

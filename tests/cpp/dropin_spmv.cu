@@ -200,6 +200,7 @@ int main() {
     algorithms::spmv::work_oriented(csr, x, y);   check("algorithms::spmv::work_oriented", y, ref);
     algorithms::spmv::thread_mapped(csr, x, y);   check("algorithms::spmv::thread_mapped", y, ref);
     algorithms::spmv::group_mapped(csr, x, y);    check("algorithms::spmv::group_mapped", y, ref);
+    algorithms::spmv::automatic(csr, x, y);       check("algorithms::spmv::automatic", y, ref);
     coo_t<int, float> coo(csr);
     algorithms::spmv::coo_thread_mapped(coo, x, y); check("algorithms::spmv::coo_thread_mapped", y, ref);
     ell_t<int, float> ell(csr);

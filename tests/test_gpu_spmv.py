@@ -322,3 +322,24 @@ def test_full_size_config2_properties(oracle):
     o = off[: n + 1].cpu().numpy()
     yo = oracle.spmv(o, idx[: o[-1]].cpu().numpy(), val[: o[-1]].cpu().numpy(), x.cpu().numpy())
     np.testing.assert_array_equal(ys["merge_path_flat"][:n].cpu().numpy(), yo)
+
+
+def test_automatic_picks_a_schedule_and_matches_the_oracle(oracle):
+    """spmv.automatic: tiny matrices and light regular rows go to
+    thread_mapped, everything else to merge_path_flat; y equals the oracle either way."""
+    from loops_b200 import csr_t
+    from loops_b200.algorithms import spmv
+    c = load_chesapeake()
+    A = csr_t(39, 39, c["off"], c["idx"], c["val"])
+    assert spmv.select_schedule(A) == "thread_mapped"
+    y = torch.full((39,), float("nan"), device="cuda")
+    spmv.automatic(A, torch.as_tensor(c["x"]).cuda(), y)
+    np.testing.assert_array_equal(y.cpu().numpy(), c["y"])
+    rows, cols = 3000, 2500
+    off, idx, val = random_csr(rows, cols, 0.01, 5, empty_every=9, heavy_row=(3, 2000), exact=True)
+    B = csr_t(rows, cols, off, idx, val)
+    assert spmv.select_schedule(B) == "merge_path_flat"       # 75 K nonzeros, a 2000-wide row
+    x = oracle.x_recipe_int(cols)
+    y = torch.full((rows,), float("nan"), device="cuda")
+    spmv.automatic(B, torch.as_tensor(x).cuda(), y)
+    np.testing.assert_array_equal(y.cpu().numpy(), oracle.spmv(off, idx, val, x))
