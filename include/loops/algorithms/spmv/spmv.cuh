@@ -207,6 +207,40 @@ util::timer_t bcsr_thread_mapped(bcsr_t<R, C, int, int, float>& bcsr, vector_t<f
   return timer;
 }
 
+// ---- fp64: the reference's entry points are templates on type_t and
+// its examples are also built for double (examples/spmv/CMakeLists.txt:29) ----
+namespace detail {
+inline util::timer_t run_f64(csr_t<int, int, double>& csr, int schedule, vector_t<double>& x, vector_t<double>& y,
+                             cudaStream_t stream) {
+  const loopsb_layout_t lay = csr.layout().descriptor();
+  util::timer_t timer(stream);
+  timer.start();
+  error::throw_if_status(loopsb_spmv_f64(&lay, schedule, raw(csr.values), raw(csr.indices), raw(x), raw(y),
+                                         static_cast<int32_t>(csr.rows), static_cast<int32_t>(csr.cols), stream),
+                         "loopsb_spmv_f64");
+  cudaStreamSynchronize(stream);
+  timer.stop();
+  return timer;
+}
+}  // namespace detail
+
+inline util::timer_t merge_path_flat(csr_t<int, int, double>& csr, vector_t<double>& x, vector_t<double>& y,
+                                     cudaStream_t stream = 0) {
+  return detail::run_f64(csr, LOOPSB_SCHED_MERGE_PATH_FLAT, x, y, stream);
+}
+inline void work_oriented(csr_t<int, int, double>& csr, vector_t<double>& x, vector_t<double>& y,
+                          cudaStream_t stream = 0) {
+  detail::run_f64(csr, LOOPSB_SCHED_WORK_ORIENTED, x, y, stream);
+}
+inline void thread_mapped(csr_t<int, int, double>& csr, vector_t<double>& x, vector_t<double>& y,
+                          cudaStream_t stream = 0) {
+  detail::run_f64(csr, LOOPSB_SCHED_THREAD_MAPPED, x, y, stream);
+}
+inline void group_mapped(csr_t<int, int, double>& csr, vector_t<double>& x, vector_t<double>& y,
+                         cudaStream_t stream = 0) {
+  detail::run_f64(csr, LOOPSB_SCHED_GROUP_MAPPED, x, y, stream);
+}
+
 /// The schedule the library would pick for this matrix (the
 /// reference publishes its heuristic's outcomes in plots/data/heuristics.csv).
 /// The widest row is computed on the device.

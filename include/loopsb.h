@@ -359,6 +359,15 @@ int loopsb_csr_to_dia_fill(int32_t num_rows, int32_t num_cols, int64_t nnz,
                            int32_t num_diagonals, int32_t* diag_offsets, float* dia_values,
                            void* stream);
 
+/* fp64 CSR SpMV (the reference builds its examples
+ * for double too, examples/spmv/CMakeLists.txt:29). thread_mapped is bit-equal to
+ * reference::spmv<double>; the other three schedules share one merge-path kernel
+ * (512 items per tile, algorithms/spmv/launch_box.hxx:68) whose rows cut by a tile
+ * boundary are accumulated with fp64 atomics. y is fully overwritten. No plan. */
+int loopsb_spmv_f64(const loopsb_layout_t* lay, int schedule, const double* values,
+                    const int32_t* col_indices, const double* x, double* y,
+                    int32_t num_rows, int32_t num_cols, void* stream);
+
 /* Which schedule to run for a CSR matrix (the
  * reference publishes the outcome of its heuristic per matrix in
  * plots/data/heuristics.csv). max_degree < 0 = unknown (then only nnz decides,

@@ -224,3 +224,25 @@ def automatic(csr: csr_t, x, y, stream=None, sync=True):
     if name is None:
         name = csr._auto_schedule = select_schedule(csr)
     return BY_NAME[name](csr, x, y, stream=stream, sync=sync)
+
+
+def spmv_f64(schedule: str, offsets, indices, values, x, y, rows: int, cols: int, stream=None, sync=True):
+    """fp64 CSR SpMV (the reference builds its examples for double too).
+    Tensors: offsets/indices int32, values/x/y float64, all on the device.
+    ``thread_mapped`` is bit-equal to reference::spmv<double>; the other three
+    schedule names share one merge-path kernel (loops_b200/csrc/spmv_f64.cu)."""
+    import torch
+    from ..layout import csr as csr_layout
+    for name, t, dt in (("offsets", offsets, torch.int32), ("indices", indices, torch.int32),
+                        ("values", values, torch.float64), ("x", x, torch.float64), ("y", y, torch.float64)):
+        if t.dtype != dt or not t.is_cuda or not t.is_contiguous():
+            raise ValueError(f"{name}: expected a contiguous {dt} device tensor")
+    if offsets.numel() != rows + 1 or x.numel() < cols or y.numel() < rows:
+        raise ValueError("shape mismatch")
+    lay = csr_layout(offsets, rows, int(indices.numel())).desc()
+    import ctypes as C
+    _lib.check(_lib.load().loopsb_spmv_f64(C.byref(lay), _lib.SCHEDULE_NAMES[schedule], _lib.ptr(values),
+                                           _lib.ptr(indices), _lib.ptr(x), _lib.ptr(y), rows, cols,
+                                           _lib.stream_ptr(stream)), "loopsb_spmv_f64")
+    if sync:
+        torch.cuda.current_stream().synchronize() if stream is None else stream.synchronize()

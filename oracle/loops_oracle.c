@@ -342,6 +342,19 @@ void orc_spmv_f64(i32 rows, const i32* off, const i32* idx, const float* val,
     y[r] = (float)sum;
   }
 }
+/* reference::spmv instantiated for double (util/reference.hxx:61-76): the same
+ * loop, every operand and the accumulator in fp64, no contraction. */
+void orc_spmv_d(i32 rows, const i32* off, const i32* idx, const double* val,
+                const double* x, double* y) {
+  for (i32 r = 0; r < rows; ++r) {
+    volatile double sum = 0.0;
+    for (i32 k = off[r]; k < off[r + 1]; ++k) {
+      volatile double p = val[k] * x[idx[k]];
+      sum = sum + p;
+    }
+    y[r] = sum;
+  }
+}
 void orc_row_l1(i32 rows, const i32* off, const i32* idx, const float* val,
                 const float* x, float* l1) {
   for (i32 r = 0; r < rows; ++r) {

@@ -127,6 +127,18 @@ void ref_spmv_f64(int rows, int cols, int nnz, const int* off, const int* idx,
   std::copy(r.begin(), r.end(), y);
 }
 
+// reference::spmv with value_t = double (what the .f64 example builds validate against)
+void ref_spmv_d(int rows, int cols, int nnz, const int* off, const int* idx,
+                const double* val, const double* x, double* y) {
+  csr_t<int, int, double, memory_space_t::host> c(rows, cols, nnz);
+  std::copy(off, off + rows + 1, c.offsets.begin());
+  std::copy(idx, idx + nnz, c.indices.begin());
+  std::copy(val, val + nnz, c.values.begin());
+  vector_t<double, memory_space_t::host> xv(x, x + cols);
+  auto r = reference::spmv(c, xv);
+  std::copy(r.begin(), r.end(), y);
+}
+
 void ref_row_l1(int rows, int cols, int nnz, const int* off, const int* idx,
                 const float* val, const float* x, float* l1) {
   csr_h c = make_csr(rows, cols, nnz, off, idx, val);

@@ -201,6 +201,31 @@ int main() {
     algorithms::spmv::thread_mapped(csr, x, y);   check("algorithms::spmv::thread_mapped", y, ref);
     algorithms::spmv::group_mapped(csr, x, y);    check("algorithms::spmv::group_mapped", y, ref);
     algorithms::spmv::automatic(csr, x, y);       check("algorithms::spmv::automatic", y, ref);
+    {  // the same entry points in double (the reference's .f64 example builds)
+      csr_t<int, int, double, memory_space_t::host> hd(rows, cols, nnz);
+      std::copy(off.begin(), off.end(), hd.offsets.begin());
+      std::copy(idx.begin(), idx.end(), hd.indices.begin());
+      std::copy(vals.begin(), vals.end(), hd.values.begin());
+      csr_t<int, int, double> cd(hd);
+      std::vector<double> xd_h(xs.begin(), xs.end());
+      vector_t<double> xd(xd_h.begin(), xd_h.end()), yd(rows);
+      std::vector<double> refd(rows, 0.0);
+      for (int r = 0; r < rows; ++r) {
+        double s = 0;
+        for (int k = off[r]; k < off[r + 1]; ++k) s += double(vals[k]) * double(xs[idx[k]]);
+        refd[r] = s;
+      }
+      auto check_d = [&](const char* name) {
+        thrust::host_vector<double> got(yd);
+        double worst = 0;
+        for (int r = 0; r < rows; ++r) worst = std::max(worst, std::fabs(got[r] - refd[r]) / std::max(1.0, std::fabs(refd[r])));
+        const bool ok = worst <= 1e-13;
+        failures += ok ? 0 : 1;
+        std::printf("%s %s (max rel err %.3g)\n", ok ? "OK" : "FAIL", name, worst);
+      };
+      algorithms::spmv::merge_path_flat(cd, xd, yd); check_d("algorithms::spmv::merge_path_flat<double>");
+      algorithms::spmv::thread_mapped(cd, xd, yd);   check_d("algorithms::spmv::thread_mapped<double>");
+    }
     coo_t<int, float> coo(csr);
     algorithms::spmv::coo_thread_mapped(coo, x, y); check("algorithms::spmv::coo_thread_mapped", y, ref);
     ell_t<int, float> ell(csr);

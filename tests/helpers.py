@@ -108,6 +108,14 @@ class Oracle:
         self.L.orc_spmv_f64(rows, P(off), P(idx), P(val), P(x), P(y))
         return y
 
+    def spmv_d(self, off, idx, val64, x64):
+        """reference::spmv<double>: fp64 values, x, accumulator and y."""
+        rows = len(off) - 1
+        y = np.zeros(rows, np.float64)
+        self.L.orc_spmv_d(rows, P(off), P(idx), P(np.ascontiguousarray(val64, np.float64)),
+                          P(np.ascontiguousarray(x64, np.float64)), P(y))
+        return y
+
     def row_l1(self, off, idx, val, x):
         rows = len(off) - 1
         y = np.zeros(rows, np.float32)

@@ -23,6 +23,18 @@ def test_validator_functions(oracle, ref_host, rows, cols, dens, seed, empty, he
 
 
 @pytest.mark.parametrize("rows,cols,dens,seed,empty,heavy", CASES)
+def test_validator_in_double(oracle, ref_host, rows, cols, dens, seed, empty, heavy):
+    """reference::spmv<double> (what the reference's .f64 example builds validate against)."""
+    off, idx, val = random_csr(rows, cols, dens, seed, empty, heavy)
+    rng = np.random.default_rng(seed + 200)
+    val64 = rng.uniform(-1.5, 1.5, len(idx))
+    x64 = rng.uniform(-2, 2, cols)
+    y = np.zeros(rows, np.float64)
+    ref_host.ref_spmv_d(rows, cols, len(idx), P(off), P(idx), P(val64), P(x64), P(y))
+    np.testing.assert_array_equal(oracle.spmv_d(off, idx, val64, x64), y)
+
+
+@pytest.mark.parametrize("rows,cols,dens,seed,empty,heavy", CASES)
 def test_conversions(oracle, ref_host, rows, cols, dens, seed, empty, heavy):
     off, idx, val = random_csr(rows, cols, dens, seed, empty, heavy)
     nnz = len(idx)
