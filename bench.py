@@ -196,7 +196,12 @@ def run_reference_arm(args, rank, world):
     emit(line)
 
 
+def dist_overlap_enabled(n):
+    return n > 1 and os.environ.get("LOOPSB_DIST_OVERLAP", "0") == "1"
+
+
 def workload_config(n):
+    overlap = dist_overlap_enabled(n)
     if n == 1:
         return {"workload": "synthetic power-law CSR 2^20 rows / 2^25 nnz fp32, merge_path_flat (BASELINE configs[1])",
                 "rows": CFG2["rows"], "nnz": CFG2["nnz"], "schedule": "merge_path_flat", "layout": "csr",
@@ -285,7 +290,7 @@ def main():
     # measured at N=2 it hides the all-gather but the two sparser SpMVs cost as much more
     # (1.588 vs 1.599 ms per step, kernels 1.70 vs 1.49 ms), so the default stays
     # all-gather -> one SpMV.
-    overlap = N > 1 and os.environ.get("LOOPSB_DIST_OVERLAP", "0") == "1"
+    overlap = dist_overlap_enabled(N)
     A_own = A_rest = y_own = plan_rest = plan_own = None
     if overlap:
         from loops_b200.dist import split_columns
