@@ -190,6 +190,16 @@ int loopsb_spmv_bcsr4x4_bf16(loopsb_plan_t* plan, const uint16_t* values_bf16,
                              const int32_t* block_col_indices,
                              const uint16_t* x_bf16_padded, float* y,
                              int32_t num_rows, void* stream);
+/* Optional, once per matrix (like loopsb_plan_tile_csr): the plan keeps a copy
+ * of the block values (and block columns) re-ordered into the tensor-core
+ * operand tiles the kernel consumes, so that a K-step's operands arrive as one
+ * TMA bulk copy. Costs 36 bytes per (padded) block of device memory and one
+ * pass over the matrix;
+ * loopsb_spmv_bcsr4x4_bf16 uses the copy whenever it is called with the same
+ * `values` pointer, and the plain path otherwise. Call again after changing
+ * the values or columns in place. Results are bit-identical either way. */
+int loopsb_plan_pack_bcsr4x4(loopsb_plan_t* plan, const uint16_t* values_bf16,
+                             const int32_t* block_col_indices, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Band-tiled plan (optional accelerator for merge_path_flat / CSR).

@@ -100,6 +100,7 @@ SIGNATURES = {
     "loopsb_spmv_bcsr_f32": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(LayoutDesc), _P, _P, _P, _P, C.c_int32, _P]),
     "loopsb_spmv_dia_f32": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _P, _P]),
     "loopsb_spmm_csr_f32": (C.c_int, [C.POINTER(LayoutDesc), _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "loopsb_plan_pack_bcsr4x4": (C.c_int, [_P, _P, _P, _P]),
     "loopsb_spmv_bcsr4x4_bf16": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P]),
     "loopsb_spmv_csr_host_f32": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.POINTER(C.c_float)]),
     "loopsb_emit_schedule": (C.c_int, [C.POINTER(LayoutDesc), C.c_int, C.c_int32, C.c_int32, C.c_int32,

@@ -182,6 +182,15 @@ def bcsr_thread_mapped(bcsr: bcsr_t, x, y, stream=None, sync=True):
             raise ValueError("x must be a CUDA bfloat16 tensor padded to num_block_cols*4")
         _check_vec("y", y, bcsr.rows)
         plan = bcsr.plan(_lib.SCHED_THREAD_MAPPED, stream)
+        # once per matrix: the plan's packed copy of the block values (TMA-fed A tiles);
+        # LOOPSB_BCSR_PACKED=0 keeps the kernel that reads the BCSR value array directly
+        import os
+        if os.environ.get("LOOPSB_BCSR_PACKED", "1") != "0" and \
+                getattr(plan, "_packed_key", None) != bcsr.values.data_ptr():
+            _lib.check(lib.loopsb_plan_pack_bcsr4x4(plan.handle, _lib.ptr(bcsr.values),
+                                                    _lib.ptr(bcsr.block_col_indices), _lib.stream_ptr(stream)),
+                       "loopsb_plan_pack_bcsr4x4")
+            plan._packed_key = bcsr.values.data_ptr()
         _lib.check(lib.loopsb_spmv_bcsr4x4_bf16(plan.handle, _lib.ptr(bcsr.values),
                                                 _lib.ptr(bcsr.block_col_indices), _lib.ptr(x),
                                                 _lib.ptr(y), bcsr.rows, _lib.stream_ptr(stream)),

@@ -1007,6 +1007,13 @@ int loopsb_spmv_bcsr4x4_bf16(loopsb_plan_t* plan, const uint16_t* values_bf16,
                       x_bf16_padded, y, num_rows, as_stream(stream));
 }
 
+int loopsb_plan_pack_bcsr4x4(loopsb_plan_t* plan, const uint16_t* values_bf16, const int32_t* block_col_indices,
+                             void* stream) {
+  LOOPSB_REQUIRE(plan != nullptr && plan->tc != nullptr,
+                 "plan was not created from a BCSR layout with thread_mapped");
+  return bcsr_tc::pack(plan->tc, values_bf16, block_col_indices, as_stream(stream));
+}
+
 int loopsb_spmv_csr_host_f32(int schedule, int32_t num_rows, int32_t num_cols,
                              int32_t nnz, const int32_t* host_offsets,
                              const int32_t* host_indices,

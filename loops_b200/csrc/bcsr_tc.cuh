@@ -60,6 +60,13 @@ struct plan_data {
   int sm_count = 0;
   int ctas_per_sm = 0;        // persistent grid = resident CTAs per SM x SMs
   long long bytes = 0;
+  // Packed copy of the block values (pack()): one 4 KB UMMA A-tile image per K-step of
+  // every work item, in the order the kernel consumes them, so a step's values arrive
+  // as ONE bulk copy instead of 128 LSU sector requests.
+  uint16_t* packed = nullptr;       // [total_tiles]{A-tile image 4 KB, 128 block columns}
+  long long* item_tile = nullptr;   // [num_items] first tile of the item
+  long long total_tiles = 0;
+  const void* packed_key = nullptr; // the values pointer the copy was made from
 };
 
 __global__ void row_lengths_kernel(const int* __restrict__ off, int n,
@@ -94,6 +101,8 @@ inline void destroy(plan_data* p) {
   if (p->item_rows) cudaFree(p->item_rows);
   if (p->split) cudaFree(p->split);
   if (p->partial) cudaFree(p->partial);
+  if (p->packed) cudaFree(p->packed);
+  if (p->item_tile) cudaFree(p->item_tile);
   delete p;
 }
 
@@ -395,6 +404,203 @@ __global__ void __launch_bounds__(kThreads)
   if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
 
+// ---------------------------------------------------------------------------
+// Packed variant: the A tiles come from the plan's packed copy by TMA bulk copy.
+// ---------------------------------------------------------------------------
+constexpr int kPackStages = 4;
+constexpr int kPackTileBytes = kATileBytes + kThreads * 4;   // A-tile image + the step's 128 block columns (-1 = none)
+
+// grid = work items, 128 threads (tid = 4*b + slot as in the SpMV kernel): writes the
+// item's A-tile images, zero where a block-row has fewer blocks than the step needs.
+__global__ void __launch_bounds__(kThreads)
+    bcsr_pack_kernel(const int4* __restrict__ items, const int4* __restrict__ item_rows,
+                     const long long* __restrict__ item_tile, const uint16_t* __restrict__ values,
+                     const int* __restrict__ block_cols, uint16_t* __restrict__ packed) {
+  const int it = blockIdx.x, tid = threadIdx.x, b = tid >> 2, slot = tid & 3;
+  const int4 item = items[it];
+  const int4 row = item_rows[(long long)it * 32 + b];
+  unsigned char* base = reinterpret_cast<unsigned char*>(packed) + size_t(item_tile[it]) * kPackTileBytes;
+  for (int s = item.y; s < item.z; ++s) {
+    const int k = 4 * s + slot;
+    uint2 v[4] = {make_uint2(0, 0), make_uint2(0, 0), make_uint2(0, 0), make_uint2(0, 0)};
+    int bc = -1;
+    if (k < row.y) {
+      bc = __ldg(block_cols + (long long)row.x + k);
+      const uint4* src = reinterpret_cast<const uint4*>(values + ((long long)row.x + k) * 16);
+      const uint4 lo = __ldg(src), hi = __ldg(src + 1);
+      v[0] = make_uint2(lo.x, lo.y); v[1] = make_uint2(lo.z, lo.w);
+      v[2] = make_uint2(hi.x, hi.y); v[3] = make_uint2(hi.z, hi.w);
+    }
+    unsigned char* tile = base + size_t(s - item.y) * kPackTileBytes;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint2*>(tile + tile_offset(4 * b + i, slot)) = v[i];
+    reinterpret_cast<int*>(tile + kATileBytes)[tid] = bc;
+  }
+}
+
+struct __align__(128) packed_stage {
+  unsigned char a[kATileBytes];
+  int cols[kThreads];
+};
+struct __align__(1024) tc_shared_packed {
+  packed_stage st[kPackStages];               // filled by one bulk copy of kPackTileBytes
+  unsigned char b[kPackStages][kBTileBytes];
+  unsigned long long full[kPackStages];       // the stage's A tile has landed (TMA complete_tx)
+  unsigned long long mma_done[kPackStages];   // the MMA that read the stage has completed
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads)
+    spmv_bcsr4x4_bf16_packed_kernel(const uint16_t* __restrict__ packed, const long long* __restrict__ item_tile,
+                                    const uint16_t* __restrict__ x, float* __restrict__ y,
+                                    const int4* __restrict__ items, int num_items, float* __restrict__ partial,
+                                    int num_rows, const int4* __restrict__ item_rows) {
+  __shared__ tc_shared_packed sm;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int b = tid >> 2;      // block-row slot inside the group
+  const int slot = tid & 3;    // block slot inside the K-step
+  constexpr uint32_t NS = kPackStages;
+
+  if (warp == 0) tmem_alloc(&sm.tmem_base, kTmemCols);
+  if (tid == 0) {
+    for (int k = 0; k < kPackStages; ++k) {
+      loops::tma::barrier_init(reinterpret_cast<uint64_t*>(&sm.full[k]), 1);
+      loops::tma::barrier_init(reinterpret_cast<uint64_t*>(&sm.mma_done[k]), 1);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+  constexpr uint32_t idesc = make_idesc(128, 32);
+  const unsigned char* packed_bytes = reinterpret_cast<const unsigned char*>(packed);
+
+  uint32_t t = 0;  // K-steps staged so far by this CTA: step t lives in stage t % NS (its (t / NS)-th use)
+
+  // x slice of the step that lives in stage `st` (its block column came with the tile)
+  auto gather = [&](uint32_t tt) {
+    const uint32_t st = tt % NS;
+    loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.full[st]), (tt / NS) & 1u);   // the tile is in
+    const int bc = sm.st[st].cols[tid];
+    return bc >= 0 ? __ldg(reinterpret_cast<const uint2*>(x + (long long)bc * 4)) : make_uint2(0, 0);
+  };
+
+  for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+    if (it + int(gridDim.x) < num_items && lane == 0) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(items + it + gridDim.x));
+      if (warp < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(item_rows + (long long)(it + gridDim.x) * 32 + 8 * warp));
+    }
+    const int4 item = __ldg(items + it);
+    const int4 row = __ldg(item_rows + (long long)it * 32 + b);
+    const int steps = item.z - item.y;
+    const unsigned char* tiles = packed_bytes + size_t(__ldg(item_tile + it)) * kPackTileBytes;
+
+    // every MMA of the previous item has completed (its epilogue waited for the last
+    // commit), so all stages are free: request the first NS tiles of this item
+    if (tid == 0) {
+      for (int j = 0; j < int(NS) && j < steps; ++j) {
+        const uint32_t st = (t + uint32_t(j)) % NS;
+        uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.full[st]);
+        loops::tma::barrier_arrive_expect_tx(bar, kPackTileBytes);
+        loops::tma::bulk_g2s(&sm.st[st], tiles + size_t(j) * kPackTileBytes, kPackTileBytes, bar);
+      }
+    }
+
+    if (steps > 0) {
+      uint2 xs = gather(t);   // step item.y
+      for (int s = item.y; s < item.z; ++s) {
+        // the x slice of the NEXT step is requested now and stored one step later
+        uint2 xn = make_uint2(0, 0);
+        if (s + 1 < item.z) xn = gather(t + 1u);
+        const uint32_t st = t % NS, use = t / NS;
+        // the MMA that last read this stage (step t - NS) must have completed before B is rewritten
+        if (use >= 1u) loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.mma_done[st]), (use - 1u) & 1u);
+        *reinterpret_cast<uint2*>(sm.b[st] + tile_offset(b, slot)) = xs;
+        loops::tma::fence_proxy_async();   // generic-proxy smem writes -> tensor-core (async) proxy
+        tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after_sync();
+          umma_bf16(tmem, make_smem_desc(sm.st[st].a, 128, 256), make_smem_desc(sm.b[st], 128, 256), idesc,
+                    s > item.y ? 1u : 0u);
+          umma_commit(reinterpret_cast<uint64_t*>(&sm.mma_done[st]));
+          // refill the stage of the PREVIOUS step (its MMA was committed one iteration ago)
+          // with the tile NS - 1 steps ahead of this one
+          const int ahead = s - 1 + int(NS);
+          if (s > item.y && ahead < item.z) {
+            const uint32_t pt = t - 1u, pst = pt % NS, puse = pt / NS;
+            loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.mma_done[pst]), puse & 1u);
+            uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.full[pst]);
+            loops::tma::barrier_arrive_expect_tx(bar, kPackTileBytes);
+            loops::tma::bulk_g2s(&sm.st[pst], tiles + size_t(ahead - item.y) * kPackTileBytes, kPackTileBytes, bar);
+          }
+        }
+        ++t;
+        xs = xn;
+      }
+    }
+
+    if (steps > 0) {
+      // accumulator complete when the last commit lands (commits complete in issue order)
+      const uint32_t lt = t - 1u;
+      loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.mma_done[lt % NS]), (lt / NS) & 1u);
+      tc_fence_after_sync();
+      uint32_t acc[8];
+      tmem_ld_32x32b_x8(tmem + (uint32_t(32 * warp) << 16) + uint32_t(8 * warp), acc);
+      const int m = 32 * warp + lane;
+      const int q = lane >> 2;
+      uint32_t o = acc[0];
+      o = q == 1 ? acc[1] : o; o = q == 2 ? acc[2] : o; o = q == 3 ? acc[3] : o; o = q == 4 ? acc[4] : o;
+      o = q == 5 ? acc[5] : o; o = q == 6 ? acc[6] : o; o = q == 7 ? acc[7] : o;
+      const float out = __uint_as_float(o);
+      if (item.w >= 0) {
+        partial[(long long)item.w * 128 + m] = out;
+      } else if (row.z >= 0) {
+        const long long yrow = (long long)row.z * 4 + (m & 3);
+        if (yrow < num_rows) y[yrow] = out;
+      }
+      tc_fence_before_sync();
+    } else {
+      const int m = 32 * warp + lane;
+      if (row.z >= 0) {
+        const long long yrow = (long long)row.z * 4 + (m & 3);
+        if (yrow < num_rows) y[yrow] = 0.0f;
+      }
+    }
+    __syncthreads();   // TMEM and all stages are free for the next item
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+// Build (or rebuild) the packed copy from `values`. One pass over the blocks.
+inline int pack(plan_data* p, const uint16_t* values, const int* block_cols, cudaStream_t stream) {
+  LOOPSB_REQUIRE(p != nullptr, "null plan");
+  if (p->num_items == 0) { p->packed_key = values; return LOOPSB_OK; }
+  LOOPSB_REQUIRE(values != nullptr && block_cols != nullptr && (reinterpret_cast<uintptr_t>(values) & 15u) == 0,
+                 "values must be 16-byte aligned");
+  if (!p->item_tile) {
+    std::vector<int4> items(size_t(p->num_items));
+    LOOPSB_CUDA_TRY(cudaMemcpy(items.data(), p->items, items.size() * sizeof(int4), cudaMemcpyDeviceToHost));
+    std::vector<long long> first(items.size());
+    long long total = 0;
+    for (size_t i = 0; i < items.size(); ++i) { first[i] = total; total += items[i].z - items[i].y; }
+    p->total_tiles = total;
+    LOOPSB_CUDA_TRY(cudaMalloc(&p->item_tile, first.size() * sizeof(long long)));
+    LOOPSB_CUDA_TRY(cudaMemcpy(p->item_tile, first.data(), first.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    LOOPSB_CUDA_TRY(cudaMalloc(&p->packed, size_t(total > 0 ? total : 1) * kPackTileBytes));
+    p->bytes += (long long)first.size() * 8 + total * kPackTileBytes;
+  }
+  bcsr_pack_kernel<<<p->num_items, kThreads, 0, stream>>>(p->items, p->item_rows, p->item_tile, values, block_cols,
+                                                          p->packed);
+  LOOPSB_CUDA_TRY(cudaGetLastError());
+  p->packed_key = values;
+  return LOOPSB_OK;
+}
+
 // y[row] = sum over the chunks of a split group, in chunk order.
 __global__ void __launch_bounds__(128)
     bcsr_split_reduce_kernel(const int4* __restrict__ split, const float* __restrict__ partial,
@@ -431,9 +637,19 @@ inline int run(plan_data* p, const loopsb_layout_t* lay, const uint16_t* values,
   }
   int grid = p->sm_count * p->ctas_per_sm;
   if (grid > p->num_items) grid = p->num_items;
-  spmv_bcsr4x4_bf16_kernel<<<grid, kThreads, 0, stream>>>(lay->offsets, block_cols, values, x, y, p->order,
-                                                        p->num_block_rows, p->items, p->num_items, p->partial,
-                                                        num_rows, p->item_rows);
+  if (p->packed && p->packed_key == values) {
+    static bool carved = false;   // 22 KB of static shared memory per CTA: ask for the large carve-out once
+    if (!carved) {
+      cudaFuncSetAttribute(spmv_bcsr4x4_bf16_packed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+      carved = true;
+    }
+    spmv_bcsr4x4_bf16_packed_kernel<<<grid, kThreads, 0, stream>>>(p->packed, p->item_tile, x, y, p->items,
+                                                                 p->num_items, p->partial, num_rows, p->item_rows);
+  } else
+    spmv_bcsr4x4_bf16_kernel<<<grid, kThreads, 0, stream>>>(lay->offsets, block_cols, values, x, y, p->order,
+                                                          p->num_block_rows, p->items, p->num_items, p->partial,
+                                                          num_rows, p->item_rows);
   LOOPSB_CUDA_TRY(cudaGetLastError());
   if (p->num_split > 0) {
     bcsr_split_reduce_kernel<<<p->num_split, 128, 0, stream>>>(p->split, p->partial, p->order, p->num_block_rows,
