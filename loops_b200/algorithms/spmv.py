@@ -157,9 +157,11 @@ def dia_thread_mapped(dia: dia_t, x, y, stream=None, sync=True):
     return timer
 
 
-def bcsr_thread_mapped(bcsr: bcsr_t, x, y, stream=None, sync=True):
+def bcsr_thread_mapped(bcsr: bcsr_t, x, y, stream=None, sync=True, repack=False):
     """fp32 blocks: one thread per block-row (the reference kernel's map).
-    bf16 4x4 blocks: the tcgen05 tensor-core kernel (BASELINE config 4).
+    bf16 4x4 blocks: the tcgen05 tensor-core kernel (BASELINE config 4); its plan
+    keeps a packed copy of the blocks (made on the first call; pass ``repack=True``
+    after changing ``bcsr.values`` / ``block_col_indices`` in place).
     ``x`` must already be padded to ``num_block_cols * C`` (bcsr.padded_x)."""
     lib = _lib.load()
     stream = stream or torch.cuda.current_stream()
@@ -186,7 +188,7 @@ def bcsr_thread_mapped(bcsr: bcsr_t, x, y, stream=None, sync=True):
         # LOOPSB_BCSR_PACKED=0 keeps the kernel that reads the BCSR value array directly
         import os
         if os.environ.get("LOOPSB_BCSR_PACKED", "1") != "0" and \
-                getattr(plan, "_packed_key", None) != bcsr.values.data_ptr():
+                (repack or getattr(plan, "_packed_key", None) != bcsr.values.data_ptr()):
             _lib.check(lib.loopsb_plan_pack_bcsr4x4(plan.handle, _lib.ptr(bcsr.values),
                                                     _lib.ptr(bcsr.block_col_indices), _lib.stream_ptr(stream)),
                        "loopsb_plan_pack_bcsr4x4")

@@ -67,6 +67,7 @@ struct plan_data {
   long long* item_tile = nullptr;   // [num_items] first tile of the item
   long long total_tiles = 0;
   const void* packed_key = nullptr; // the values pointer the copy was made from
+  int* work_counter = nullptr;      // next work item to hand out (packed kernel: dynamic, longest first)
 };
 
 __global__ void row_lengths_kernel(const int* __restrict__ off, int n,
@@ -103,6 +104,7 @@ inline void destroy(plan_data* p) {
   if (p->partial) cudaFree(p->partial);
   if (p->packed) cudaFree(p->packed);
   if (p->item_tile) cudaFree(p->item_tile);
+  if (p->work_counter) cudaFree(p->work_counter);
   delete p;
 }
 
@@ -407,7 +409,8 @@ __global__ void __launch_bounds__(kThreads)
 // ---------------------------------------------------------------------------
 // Packed variant: the A tiles come from the plan's packed copy by TMA bulk copy.
 // ---------------------------------------------------------------------------
-constexpr int kPackStages = 4;
+constexpr int kPackStages = 5;   // tiles in flight per CTA (23 KB); x slices are gathered two steps ahead
+constexpr int kPackBStages = 3;  // B tiles (x slices) only have to outlive their own MMA
 constexpr int kPackTileBytes = kATileBytes + kThreads * 4;   // A-tile image + the step's 128 block columns (-1 = none)
 
 // grid = work items, 128 threads (tid = 4*b + slot as in the SpMV kernel): writes the
@@ -442,25 +445,26 @@ struct __align__(128) packed_stage {
   unsigned char a[kATileBytes];
   int cols[kThreads];
 };
-struct __align__(1024) tc_shared_packed {
+struct __align__(128) tc_shared_packed {
   packed_stage st[kPackStages];               // filled by one bulk copy of kPackTileBytes
-  unsigned char b[kPackStages][kBTileBytes];
+  unsigned char b[kPackBStages][kBTileBytes];
   unsigned long long full[kPackStages];       // the stage's A tile has landed (TMA complete_tx)
   unsigned long long mma_done[kPackStages];   // the MMA that read the stage has completed
   uint32_t tmem_base;
+  int next_item;                              // handed out by the work counter, one item ahead
 };
 
 __global__ void __launch_bounds__(kThreads)
     spmv_bcsr4x4_bf16_packed_kernel(const uint16_t* __restrict__ packed, const long long* __restrict__ item_tile,
                                     const uint16_t* __restrict__ x, float* __restrict__ y,
                                     const int4* __restrict__ items, int num_items, float* __restrict__ partial,
-                                    int num_rows, const int4* __restrict__ item_rows) {
+                                    int num_rows, const int4* __restrict__ item_rows, int* __restrict__ work_counter) {
   __shared__ tc_shared_packed sm;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int b = tid >> 2;      // block-row slot inside the group
   const int slot = tid & 3;    // block slot inside the K-step
-  constexpr uint32_t NS = kPackStages;
+  constexpr uint32_t NS = kPackStages, NB = kPackBStages;
 
   if (warp == 0) tmem_alloc(&sm.tmem_base, kTmemCols);
   if (tid == 0) {
@@ -486,11 +490,10 @@ __global__ void __launch_bounds__(kThreads)
     return bc >= 0 ? __ldg(reinterpret_cast<const uint2*>(x + (long long)bc * 4)) : make_uint2(0, 0);
   };
 
-  for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
-    if (it + int(gridDim.x) < num_items && lane == 0) {
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(items + it + gridDim.x));
-      if (warp < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(item_rows + (long long)(it + gridDim.x) * 32 + 8 * warp));
-    }
+  // Work items are sorted longest first and handed out dynamically (a static deal leaves
+  // the busiest CTA with ~20 % more K-steps than the average): the first item is the
+  // CTA's own index, every further one comes from the counter, fetched one item ahead.
+  for (int it = blockIdx.x; it < num_items;) {
     const int4 item = __ldg(items + it);
     const int4 row = __ldg(item_rows + (long long)it * 32 + b);
     const int steps = item.z - item.y;
@@ -507,22 +510,47 @@ __global__ void __launch_bounds__(kThreads)
       }
     }
 
+    // the first tiles of this CTA's NEXT item go to L2 now, so that its start pays an L2
+    // hit instead of an HBM round trip (one bulk prefetch per tile, issued by one thread)
+    if (tid == 32) {
+      const int nxt = int(gridDim.x) + atomicAdd(work_counter, 1);
+      sm.next_item = nxt;   // read by everybody after the item's last barrier
+      if (nxt < num_items) {
+        const int4 nitem = __ldg(items + nxt);
+        const unsigned char* ntiles = packed_bytes + size_t(__ldg(item_tile + nxt)) * kPackTileBytes;
+        const int n = min(3, nitem.z - nitem.y);
+        for (int j = 0; j < n; ++j)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ntiles + size_t(j) * kPackTileBytes),
+                       "r"(uint32_t(kPackTileBytes)) : "memory");
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(item_rows + (long long)nxt * 32));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(item_rows + (long long)nxt * 32 + 8));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(item_rows + (long long)nxt * 32 + 16));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(item_rows + (long long)nxt * 32 + 24));
+      }
+    }
+
     if (steps > 0) {
       uint2 xs = gather(t);   // step item.y
+      uint2 xn = make_uint2(0, 0);
+      if (item.y + 1 < item.z) xn = gather(t + 1u);
       for (int s = item.y; s < item.z; ++s) {
-        // the x slice of the NEXT step is requested now and stored one step later
-        uint2 xn = make_uint2(0, 0);
-        if (s + 1 < item.z) xn = gather(t + 1u);
-        const uint32_t st = t % NS, use = t / NS;
-        // the MMA that last read this stage (step t - NS) must have completed before B is rewritten
-        if (use >= 1u) loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.mma_done[st]), (use - 1u) & 1u);
-        *reinterpret_cast<uint2*>(sm.b[st] + tile_offset(b, slot)) = xs;
+        // the x slice of step s + 2 is requested now and stored two steps later (its tile
+        // was requested at least NS - 3 steps ago)
+        uint2 xnn = make_uint2(0, 0);
+        if (s + 2 < item.z) xnn = gather(t + 2u);
+        const uint32_t st = t % NS, bst = t % NB;
+        // the MMA that last read this B tile (step t - NB) must have completed before it is rewritten
+        if (t >= NB) {
+          const uint32_t pt = t - NB;
+          loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.mma_done[pt % NS]), (pt / NS) & 1u);
+        }
+        *reinterpret_cast<uint2*>(sm.b[bst] + tile_offset(b, slot)) = xs;
         loops::tma::fence_proxy_async();   // generic-proxy smem writes -> tensor-core (async) proxy
         tc_fence_before_sync();
         __syncthreads();
         if (tid == 0) {
           tc_fence_after_sync();
-          umma_bf16(tmem, make_smem_desc(sm.st[st].a, 128, 256), make_smem_desc(sm.b[st], 128, 256), idesc,
+          umma_bf16(tmem, make_smem_desc(sm.st[st].a, 128, 256), make_smem_desc(sm.b[bst], 128, 256), idesc,
                     s > item.y ? 1u : 0u);
           umma_commit(reinterpret_cast<uint64_t*>(&sm.mma_done[st]));
           // refill the stage of the PREVIOUS step (its MMA was committed one iteration ago)
@@ -538,6 +566,7 @@ __global__ void __launch_bounds__(kThreads)
         }
         ++t;
         xs = xn;
+        xn = xnn;
       }
     }
 
@@ -569,6 +598,8 @@ __global__ void __launch_bounds__(kThreads)
       }
     }
     __syncthreads();   // TMEM and all stages are free for the next item
+    it = sm.next_item;
+    __syncthreads();   // everybody has read it before thread 32 overwrites it
   }
 
   tc_fence_before_sync();
@@ -627,7 +658,7 @@ inline int run(plan_data* p, const loopsb_layout_t* lay, const uint16_t* values,
   LOOPSB_REQUIRE((reinterpret_cast<uintptr_t>(values) & 15u) == 0 && (reinterpret_cast<uintptr_t>(x) & 7u) == 0,
                  "values must be 16-byte and x 8-byte aligned");
   if (p->ctas_per_sm == 0) {
-    // persistent grid: 8 CTAs per SM measured best on B200 (tools/bcsr_bench.py: 6 -> 137 us,
+    // persistent grid: 8 CTAs per SM measured best on B200 for the direct kernel (tools/bcsr_bench.py: 6 -> 137 us,
     // 8 -> 130 us, 10 -> 147 us, 12 -> 139 us)
     // (cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for this kernel on
     // B200 -- it is not used; 56 registers x 128 threads and 11 KB leave room for 9.)
@@ -635,17 +666,22 @@ inline int run(plan_data* p, const loopsb_layout_t* lay, const uint16_t* values,
     if (const char* e = getenv("LOOPSB_BCSR_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
     p->ctas_per_sm = per_sm;
   }
+  const bool use_packed = p->packed && p->packed_key == values;
+  // (the packed kernel holds 26 KB of shared memory per CTA: 8 still fit on an SM)
   int grid = p->sm_count * p->ctas_per_sm;
   if (grid > p->num_items) grid = p->num_items;
-  if (p->packed && p->packed_key == values) {
+  if (use_packed) {
     static bool carved = false;   // 22 KB of static shared memory per CTA: ask for the large carve-out once
     if (!carved) {
       cudaFuncSetAttribute(spmv_bcsr4x4_bf16_packed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                            cudaSharedmemCarveoutMaxShared);
       carved = true;
     }
+    if (!p->work_counter) LOOPSB_CUDA_TRY(cudaMalloc(&p->work_counter, 4));
+    LOOPSB_CUDA_TRY(cudaMemsetAsync(p->work_counter, 0, 4, stream));
     spmv_bcsr4x4_bf16_packed_kernel<<<grid, kThreads, 0, stream>>>(p->packed, p->item_tile, x, y, p->items,
-                                                                 p->num_items, p->partial, num_rows, p->item_rows);
+                                                                 p->num_items, p->partial, num_rows, p->item_rows,
+                                                                 p->work_counter);
   } else
     spmv_bcsr4x4_bf16_kernel<<<grid, kThreads, 0, stream>>>(lay->offsets, block_cols, values, x, y, p->order,
                                                           p->num_block_rows, p->items, p->num_items, p->partial,

@@ -96,3 +96,31 @@ def test_fp32_blocks_still_use_thread_mapped(oracle, battery):
     g_off, g_col, g_val = b["bcsr4"]
     xp = np.zeros(((b["cols"] + 3) // 4) * 4, np.float32); xp[: b["cols"]] = b["x"]
     np.testing.assert_array_equal(y.cpu().numpy(), oracle.spmv_bcsr(4, 4, b["rows"], g_off, g_col, g_val, xp))
+
+
+def test_packed_and_direct_paths_are_bit_identical(monkeypatch):
+    """The plan's packed copy (A-tile images + block columns, one TMA bulk copy per
+    K-step, dynamic work items) and the kernel that reads the BCSR arrays directly
+    run the same MMAs in the same order: y must be equal bit for bit -- also after
+    the values change in place and the copy is rebuilt."""
+    from loops_b200 import csr_t, bcsr_t
+    from loops_b200.algorithms import spmv
+    rows, cols = 4103, 3001                     # ragged last block-row / block-column
+    off, idx, val = random_csr(rows, cols, 0.012, 77, empty_every=6, heavy_row=(9, 2500))
+    A = csr_t(rows, cols, off, idx, val)
+    B = bcsr_t.from_csr(A, 4, 4, value_dtype=torch.bfloat16)
+    xb = B.padded_x(torch.as_tensor(np.random.default_rng(5).uniform(-1, 1, cols).astype(np.float32)).cuda()
+                    .to(torch.bfloat16))
+    yd = torch.full((rows,), float("nan"), device="cuda")
+    yp = torch.full((rows,), float("nan"), device="cuda")
+    monkeypatch.setenv("LOOPSB_BCSR_PACKED", "0")
+    spmv.bcsr_thread_mapped(B, xb, yd)
+    monkeypatch.setenv("LOOPSB_BCSR_PACKED", "1")
+    spmv.bcsr_thread_mapped(B, xb, yp)
+    assert torch.equal(yd, yp) and bool(torch.isfinite(yp).all())
+    B.values.mul_(0.5)                          # in place: same pointer, new numbers
+    spmv.bcsr_thread_mapped(B, xb, yp, repack=True)
+    assert torch.equal(yp, yd * 0.5)
+    for _ in range(3):                          # the work counter is re-armed every launch
+        spmv.bcsr_thread_mapped(B, xb, yp)
+    assert torch.equal(yp, yd * 0.5)
