@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(kThreads)
 // Packed variant: the A tiles come from the plan's packed copy by TMA bulk copy.
 // ---------------------------------------------------------------------------
 constexpr int kPackStages = 5;   // tiles in flight per CTA (23 KB); x slices are gathered two steps ahead
-constexpr int kPackBStages = 3;  // B tiles (x slices) only have to outlive their own MMA
+constexpr int kPackBStages = 4;  // B tiles: steps s, s+1, s+2 being filled / read, s-1 still under its MMA
 constexpr int kPackTileBytes = kATileBytes + kThreads * 4;   // A-tile image + the step's 128 block columns (-1 = none)
 
 // grid = work items, 128 threads (tid = 4*b + slot as in the SpMV kernel): writes the
@@ -482,13 +482,25 @@ __global__ void __launch_bounds__(kThreads)
 
   uint32_t t = 0;  // K-steps staged so far by this CTA: step t lives in stage t % NS (its (t / NS)-th use)
 
-  // x slice of the step that lives in stage `st` (its block column came with the tile)
-  auto gather = [&](uint32_t tt) {
-    const uint32_t st = tt % NS;
-    loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.full[st]), (tt / NS) & 1u);   // the tile is in
+  // The x slice of step tt goes from global memory straight into its B tile with an
+  // 8-byte cp.async (zero-filled when the slot holds no block). Nothing lands in
+  // registers, so the generic->async proxy fence of an earlier step does not have to
+  // wait for the gathers of later steps (with register-staged slices it did: ncu showed
+  // the fence stalled on the long scoreboard of the look-ahead loads).
+  auto issue_x = [&](uint32_t tt) {
+    const uint32_t st = tt % NS, bst = tt % NB;
+    loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.full[st]), (tt / NS) & 1u);   // the tile (and its columns) is in
+    if (tt >= NB) {   // the MMA that last read this B tile (step tt - NB) has completed
+      const uint32_t pt = tt - NB;
+      loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.mma_done[pt % NS]), (pt / NS) & 1u);
+    }
     const int bc = sm.st[st].cols[tid];
-    return bc >= 0 ? __ldg(reinterpret_cast<const uint2*>(x + (long long)bc * 4)) : make_uint2(0, 0);
+    const uint32_t dst = loops::tma::smem_addr(sm.b[bst] + tile_offset(b, slot));
+    const uint16_t* src = x + (long long)(bc >= 0 ? bc : 0) * 4;
+    const uint32_t nbytes = bc >= 0 ? 8u : 0u;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
   };
+  auto commit_x = []() { asm volatile("cp.async.commit_group;" ::: "memory"); };
 
   // Work items are sorted longest first and handed out dynamically (a static deal leaves
   // the busiest CTA with ~20 % more K-steps than the average): the first item is the
@@ -530,21 +542,15 @@ __global__ void __launch_bounds__(kThreads)
     }
 
     if (steps > 0) {
-      uint2 xs = gather(t);   // step item.y
-      uint2 xn = make_uint2(0, 0);
-      if (item.y + 1 < item.z) xn = gather(t + 1u);
+      // one cp.async group per K-step, two steps of look-ahead
+      issue_x(t); commit_x();
+      if (item.y + 1 < item.z) issue_x(t + 1u);
+      commit_x();
       for (int s = item.y; s < item.z; ++s) {
-        // the x slice of step s + 2 is requested now and stored two steps later (its tile
-        // was requested at least NS - 3 steps ago)
-        uint2 xnn = make_uint2(0, 0);
-        if (s + 2 < item.z) xnn = gather(t + 2u);
+        if (s + 2 < item.z) issue_x(t + 2u);
+        commit_x();
+        asm volatile("cp.async.wait_group 2;" ::: "memory");   // this step's slice has landed
         const uint32_t st = t % NS, bst = t % NB;
-        // the MMA that last read this B tile (step t - NB) must have completed before it is rewritten
-        if (t >= NB) {
-          const uint32_t pt = t - NB;
-          loops::tma::barrier_wait(reinterpret_cast<uint64_t*>(&sm.mma_done[pt % NS]), (pt / NS) & 1u);
-        }
-        *reinterpret_cast<uint2*>(sm.b[bst] + tile_offset(b, slot)) = xs;
         loops::tma::fence_proxy_async();   // generic-proxy smem writes -> tensor-core (async) proxy
         tc_fence_before_sync();
         __syncthreads();
@@ -565,9 +571,8 @@ __global__ void __launch_bounds__(kThreads)
           }
         }
         ++t;
-        xs = xn;
-        xn = xnn;
       }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
 
     if (steps > 0) {
@@ -667,8 +672,8 @@ inline int run(plan_data* p, const loopsb_layout_t* lay, const uint16_t* values,
     p->ctas_per_sm = per_sm;
   }
   const bool use_packed = p->packed && p->packed_key == values;
-  // (the packed kernel holds 26 KB of shared memory per CTA: 8 still fit on an SM)
-  int grid = p->sm_count * p->ctas_per_sm;
+  // the packed kernel holds 28 KB of shared memory per CTA: 7 fit on an SM
+  int grid = p->sm_count * (use_packed && !getenv("LOOPSB_BCSR_CTAS") ? 7 : p->ctas_per_sm);
   if (grid > p->num_items) grid = p->num_items;
   if (use_packed) {
     static bool carved = false;   // 22 KB of static shared memory per CTA: ask for the large carve-out once
