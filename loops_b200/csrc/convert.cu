@@ -200,23 +200,26 @@ __global__ void bcsr_fill_kernel(int64_t n, int R, int C, const int* __restrict_
 }
 
 // ---- csr -> dia -------------------------------------------------------------
-__global__ void diag_flags_kernel(int64_t n, int rows, const int* __restrict__ rowid, const int* __restrict__ col,
-                                  int* __restrict__ flag) {
+__global__ void diag_flags_kernel(int64_t n, int rows, int cols, const int* __restrict__ rowid,
+                                  const int* __restrict__ col, int* __restrict__ flag) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) flag[col[i] - rowid[i] + (rows - 1)] = 1;
+  if (i >= n) return;
+  const int c = col[i];
+  if (c >= 0 && c < cols) flag[c - rowid[i] + (rows - 1)] = 1;   // a column outside the matrix is ignored, never an OOB write
 }
 __global__ void diag_compact_kernel(int nkeys, int rows, const int* __restrict__ flag, const int* __restrict__ pos,
                                     int* __restrict__ diag_offsets) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < nkeys && flag[k]) diag_offsets[pos[k]] = k - (rows - 1);
 }
-__global__ void dia_fill_kernel(int64_t n, int rows, const int* __restrict__ rowid, const int* __restrict__ col,
-                                const float* __restrict__ val, const int* __restrict__ pos,
-                                float* __restrict__ values) {
+__global__ void dia_fill_kernel(int64_t n, int rows, int cols, const int* __restrict__ rowid,
+                                const int* __restrict__ col, const float* __restrict__ val,
+                                const int* __restrict__ pos, float* __restrict__ values) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int r = rowid[i];
-  values[size_t(pos[col[i] - r + (rows - 1)]) * size_t(rows) + size_t(r)] = val[i];
+  const int r = rowid[i], c = col[i];
+  if (c < 0 || c >= cols) return;
+  values[size_t(pos[c - r + (rows - 1)]) * size_t(rows) + size_t(r)] = val[i];
 }
 
 // presence flags over (col - row) and their exclusive scan; returns the count
@@ -228,7 +231,7 @@ int diag_scan(int rows, int cols, int64_t nnz, const int* off, const int* idx, d
   CONV_ALLOC(pos, size_t(nkeys) * 4);
   if (int st = expand_rows(rows, nnz, off, rowid.as<int>(), s)) return st;
   LOOPSB_CUDA_TRY(cudaMemsetAsync(flag.p, 0, size_t(nkeys) * 4, s));
-  diag_flags_kernel<<<blocks_for(nnz), kThreads, 0, s>>>(nnz, rows, rowid.as<int>(), idx, flag.as<int>());
+  diag_flags_kernel<<<blocks_for(nnz), kThreads, 0, s>>>(nnz, rows, cols, rowid.as<int>(), idx, flag.as<int>());
   size_t bytes = 0;
   LOOPSB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, bytes, flag.as<int>(), pos.as<int>(), nkeys, s));
   dbuf tmp;
@@ -464,7 +467,7 @@ int loopsb_csr_to_dia_fill(int32_t num_rows, int32_t num_cols, int64_t nnz, cons
   diag_compact_kernel<<<blocks_for(nkeys), kThreads, 0, s>>>(nkeys, num_rows, flag.as<int>(), pos.as<int>(),
                                                               diag_offsets);
   LOOPSB_CUDA_TRY(cudaMemsetAsync(dia_values, 0, size_t(nd) * size_t(num_rows) * 4, s));
-  dia_fill_kernel<<<blocks_for(nnz), kThreads, 0, s>>>(nnz, num_rows, rowid.as<int>(), indices, values,
+  dia_fill_kernel<<<blocks_for(nnz), kThreads, 0, s>>>(nnz, num_rows, num_cols, rowid.as<int>(), indices, values,
                                                         pos.as<int>(), dia_values);
   LOOPSB_CUDA_TRY(cudaGetLastError());
   LOOPSB_CUDA_TRY(cudaStreamSynchronize(s));

@@ -1,3 +1,6 @@
+"""tools/bcsr_uniform.py -- BCSR 4x4 bf16 tcgen05 on matrices whose block-rows all have the
+same length (8 / 32 / 64 blocks): separates the per-work-item cost from the per-K-step cost
+(DESIGN 4.3). Back-to-back time of the packed and the direct kernel."""
 import sys, os
 sys.path.insert(0, "/root/repo")
 import numpy as np, torch
