@@ -533,7 +533,7 @@ def main():
                    "x from pinned host memory and downloads y; `value` overlaps the copies of neighbouring "
                    "steps on side streams (4 buffers in flight; at N=1 issued through the CUDA runtime and the "
                    "C ABI directly, as a C caller would), `serial_value` runs copy-in/SpMV/copy-out back to "
-                   "back; wall clock, final synchronize on all streams; median of three repetitions of the K-step loop"}
+                   "back; wall clock, final synchronize on all streams; median of three repetitions of the K-step loop. On the pool's (virtualised, one NUMA node) boxes this figure is bimodal from PROCESS to process -- ~95 us or ~130 us per step, stable within a process, unaffected by CPU affinity or GC -- i.e. it follows the host's PCIe path, not this code"}
     y_e2e_ok = bool(torch.equal(torch.from_numpy(y_host[(args.steps - 1) % NBUF].numpy()).to(dev), yd[(args.steps - 1) % NBUF]))
 
     # correctness guard on the timed configuration (exact inputs -> exact sums)
