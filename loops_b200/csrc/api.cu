@@ -4,6 +4,7 @@
 
 #include "common.cuh"
 #include "spmv_merge.cuh"
+#include "spmv_merge2.cuh"
 #include "spmv_schedules.cuh"
 #include "bcsr_tc.cuh"
 #include "spmv_tiled.cuh"
@@ -136,6 +137,83 @@ int merge_variant_from_env() {
   int v = atoi(e);
   return (v >= 0 && v < kNumMergeVariants) ? v : kDefault;
 }
+
+// Second-generation merge-path kernel (spmv_merge2.cuh): {CTA threads, target CTAs/SM}.
+struct merge2_variant {
+  int threads, ctas_per_sm, smem, carveout_kb;
+  void (*launch)(bool array_ends, bool accumulate, int grid, int smem, cudaStream_t s, const int* row_end, int pitch,
+                 const int* indices, const float* values, const float* x, float* y, const int2* coords,
+                 int M, int T, int A, int nct, int* carry_row, float* carry_val);
+  cudaError_t (*prepare)(int smem);
+};
+
+template <int THREADS, int MINB, int STAGES>
+struct merge2_inst {
+  using shared_t = mp2::shared_t<THREADS, STAGES>;
+  static void launch(bool array_ends, bool accumulate, int grid, int smem, cudaStream_t s, const int* row_end,
+                     int pitch, const int* indices, const float* values, const float* x, float* y,
+                     const int2* coords, int M, int T, int A, int nct, int* carry_row, float* carry_val) {
+    if (array_ends && accumulate)
+      mp2::spmv_merge2_kernel<THREADS, MINB, STAGES, true, true><<<grid, THREADS, smem, s>>>(
+          row_end, pitch, indices, values, x, y, coords, M, T, A, nct, carry_row, carry_val);
+    else if (array_ends)
+      mp2::spmv_merge2_kernel<THREADS, MINB, STAGES, true, false><<<grid, THREADS, smem, s>>>(
+          row_end, pitch, indices, values, x, y, coords, M, T, A, nct, carry_row, carry_val);
+    else
+      mp2::spmv_merge2_kernel<THREADS, MINB, STAGES, false, false><<<grid, THREADS, smem, s>>>(
+          row_end, pitch, indices, values, x, y, coords, M, T, A, nct, carry_row, carry_val);
+  }
+  static constexpr int carveout_kb() {
+    const int need = (MINB * (int(sizeof(shared_t)) + 1024) + 1023) / 1024;
+    const int buckets[] = {8, 16, 32, 64, 100, 132, 164, 196, 228};
+    for (int b : buckets) if (need <= b) return b;
+    return 228;
+  }
+  static cudaError_t prepare(int smem) {
+    const void* ks[] = {reinterpret_cast<const void*>(mp2::spmv_merge2_kernel<THREADS, MINB, STAGES, true, false>),
+                        reinterpret_cast<const void*>(mp2::spmv_merge2_kernel<THREADS, MINB, STAGES, true, true>),
+                        reinterpret_cast<const void*>(mp2::spmv_merge2_kernel<THREADS, MINB, STAGES, false, false>)};
+    const int pct = (carveout_kb() * 100 + 227) / 228;
+    for (const void* k : ks) {
+      cudaError_t e;
+      if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
+  static constexpr merge2_variant variant() {
+    return merge2_variant{THREADS, MINB, int(sizeof(shared_t)), carveout_kb(), &launch, &prepare};
+  }
+};
+
+const merge2_variant kMerge2Variants[] = {
+    merge2_inst<128, 6, 2>::variant(),  // 0: 128 thr, 2 chunks/thread, 6 CTAs/SM, two bulk-copy stages (default)
+    merge2_inst<128, 5, 2>::variant(),  // 1
+    merge2_inst<128, 4, 2>::variant(),  // 2: fewer CTAs, more L1 -- ahead when x is far larger than an L2 partition
+    merge2_inst<128, 6, 1>::variant(),  // 3: one stage (measured: the re-fill does not land in time, 183 vs 161 us)
+    merge2_inst<256, 3, 2>::variant(),  // 4: 256 thr, 1 chunk/thread
+    merge2_inst<128, 7, 2>::variant(),  // 5
+};
+constexpr int kNumMerge2Variants = int(sizeof(kMerge2Variants) / sizeof(kMerge2Variants[0]));
+
+// LOOPSB_MERGE_KERNEL=1 keeps the first-generation kernel (tuning / A-B aid).
+int merge_generation_from_env() {
+  const char* e = getenv("LOOPSB_MERGE_KERNEL");
+  return (e && atoi(e) == 1) ? 1 : 2;
+}
+int merge2_variant_from_env() {
+  // -1 = decide per call from the size of x (see merge2_pick)
+  const char* e = getenv("LOOPSB_MERGE2_VARIANT");
+  if (!e) return -1;
+  int v = atoi(e);
+  return (v >= 0 && v < kNumMerge2Variants) ? v : -1;
+}
+// Measured on B200 (profiles/merge_probe_r02.txt): 6 CTAs/SM for config 2 (x = 4 MB,
+// 161 vs 170 us), 4 CTAs/SM for the multi-GPU shards (x = 64 MB, 345 vs 355 us).
+inline int merge2_pick(int forced, size_t x_bytes) {
+  if (forced >= 0) return forced;
+  return x_bytes >= (size_t(32) << 20) ? 2 : 0;
+}
 }  // namespace
 
 struct loopsb_plan {
@@ -148,6 +226,8 @@ struct loopsb_plan {
   long long M = 0;
   int num_cta_tiles = 0;
   int variant = 0;
+  int gen = 1;        // merge kernel generation (2 = spmv_merge2.cuh, needs 16-byte aligned arrays)
+  int variant2 = -1;  // index into kMerge2Variants forced by LOOPSB_MERGE2_VARIANT, -1 = pick per call
   int wo_grid = 0;   // work_oriented: reference-style grid (blocks of 128 threads)
   long long* phases = nullptr;  // LOOPSB_DEBUG_PHASES=1: per-CTA phase cycle counters
   int* carry_row = nullptr;
@@ -200,6 +280,29 @@ void free_probes(loopsb_plan* p) {
 }  // namespace
 
 namespace {
+cudaError_t prepare_merge2(int forced) {
+  for (int v = 0; v < kNumMerge2Variants; ++v) {
+    if (forced >= 0 ? v != forced : (v != merge2_pick(-1, 0) && v != merge2_pick(-1, size_t(1) << 40))) continue;
+    cudaError_t e = kMerge2Variants[v].prepare(kMerge2Variants[v].smem);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+// Second-generation merge-path launch (merge_path_flat / ell_merge_path / work_oriented tiles).
+void launch_merge2(const loopsb_plan* plan, bool array_ends, bool accumulate, cudaStream_t s,
+                   const int32_t* col_indices, const float* values, const float* x, float* y, int32_t num_cols) {
+  const merge2_variant& m2 = kMerge2Variants[merge2_pick(plan->variant2, size_t(num_cols) * sizeof(float))];
+  const int grid = std::min(m2.ctas_per_sm * plan->sm_count, plan->num_cta_tiles);
+  m2.launch(array_ends, accumulate, grid, m2.smem, s, array_ends ? plan->lay.offsets + 1 : nullptr, plan->lay.pitch,
+            col_indices, values, x, y, plan->coords, int(plan->M), plan->lay.num_tiles, plan->lay.num_atoms,
+            plan->num_cta_tiles, plan->carry_row, plan->carry_val);
+}
+
+inline bool aligned16(const void* a, const void* b) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15u) == 0;
+}
+
 int launch_tiled(bt::plan_data* d, const float* x, float* y, cudaStream_t s) {
   bt::params p;
   p.steps = d->steps; p.steps_end = d->steps + size_t(d->total_steps + d->g.es) * bt::kStepWords; p.stream_base = d->stream_base; p.blk_begin = d->blk_begin; 
@@ -613,7 +716,9 @@ int loopsb_plan_create(loopsb_plan_t** out, const loopsb_layout_t* lay,
     }
     const long long W = (long long)T + A;
     p->M = (W + mp::kRefItemsPerMergeTile - 1) / mp::kRefItemsPerMergeTile;
+    p->gen = merge_generation_from_env();
     p->variant = merge_variant_from_env();
+    if (p->gen == 2 && kMergeVariants[p->variant].g != 1) p->variant = 9;   // fallback kernel shares the 1-tile carries
     const merge_variant& mv = kMergeVariants[p->variant];
     p->num_cta_tiles = int((p->M + mv.g - 1) / mv.g);
     p->cta_threads = mv.threads;
@@ -622,6 +727,9 @@ int loopsb_plan_create(loopsb_plan_t** out, const loopsb_layout_t* lay,
     int grid = mv.ctas_per_sm * dp->sm_count;
     if (grid > p->num_cta_tiles) grid = p->num_cta_tiles;
     p->grid = grid;
+    if (p->gen == 2) {
+      p->variant2 = merge2_variant_from_env();
+    }
     if (p->M > 0) {
       const size_t cbytes = size_t(p->M + 1) * sizeof(int2);
       const size_t nct = size_t(p->num_cta_tiles);
@@ -653,9 +761,16 @@ int loopsb_plan_create(loopsb_plan_t** out, const loopsb_layout_t* lay,
           cudaMemsetAsync(p->phases, 0, size_t(p->grid) * 8 * sizeof(long long), s);
         }
       }
-      if (mv.prepare(p->smem_bytes) != cudaSuccess) {
+      if (mv.prepare(p->smem_bytes) != cudaSuccess ||
+          (p->gen == 2 && prepare_merge2(p->variant2) != cudaSuccess)) {
         set_error("cannot opt in to %d bytes of dynamic shared memory", p->smem_bytes);
         (void)cudaGetLastError();
+        return fail(LOOPSB_ERR_CUDA);
+      }
+      // The coordinates are written on `s`; SpMV calls may come on any stream
+      // (the Python mirror caches plans per container): finish them here.
+      if (cudaStreamSynchronize(s) != cudaSuccess) {
+        set_error("merge-path plan set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(LOOPSB_ERR_CUDA);
       }
     }
@@ -713,6 +828,7 @@ int loopsb_plan_create(loopsb_plan_t** out, const loopsb_layout_t* lay,
       }
       diags.push_back(W);
     }
+    p->gen = merge_generation_from_env();
     p->variant = merge_variant_from_env();
     const merge_variant& mv = kMergeVariants[p->variant];
     if (mv.g != 1) { p->variant = 9; }
@@ -725,6 +841,9 @@ int loopsb_plan_create(loopsb_plan_t** out, const loopsb_layout_t* lay,
     int grid = mv1.ctas_per_sm * dp->sm_count;
     if (grid > p->num_cta_tiles) grid = p->num_cta_tiles;
     p->grid = grid;
+    if (p->gen == 2) {
+      p->variant2 = merge2_variant_from_env();
+    }
     if (p->M > 0) {
       long long* d_diags = nullptr;
       const size_t nct = size_t(p->num_cta_tiles);
@@ -743,7 +862,8 @@ int loopsb_plan_create(loopsb_plan_t** out, const loopsb_layout_t* lay,
           lay->offsets + 1, 0, T, A, 0, int(p->M), p->coords, d_diags);
       cudaError_t e = cudaStreamSynchronize(s);   // diags (host vector) and d_diags die here
       cudaFree(d_diags);
-      if (e != cudaSuccess || mv1.prepare(p->smem_bytes) != cudaSuccess) {
+      if (e != cudaSuccess || mv1.prepare(p->smem_bytes) != cudaSuccess ||
+          (p->gen == 2 && prepare_merge2(p->variant2) != cudaSuccess)) {
         set_error("work_oriented plan set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
         return fail(LOOPSB_ERR_CUDA);
       }
@@ -762,10 +882,13 @@ int loopsb_plan_info(const loopsb_plan_t* plan, loopsb_plan_info_t* info) {
   info->threads_per_block = 128;
   info->items_per_thread = plan->schedule == LOOPSB_SCHED_MERGE_PATH_FLAT ? 8 : 1;
   info->num_merge_tiles = plan->M;
-  info->grid_blocks = plan->grid;
-  info->cta_threads = plan->cta_threads;
+  const bool gen2 = plan->gen == 2 && (plan->schedule == LOOPSB_SCHED_MERGE_PATH_FLAT ||
+                                       plan->schedule == LOOPSB_SCHED_WORK_ORIENTED);
+  const merge2_variant& m2 = kMerge2Variants[merge2_pick(plan->variant2, 0)];   // geometry for an L2-sized x
+  info->grid_blocks = gen2 ? std::min(m2.ctas_per_sm * plan->sm_count, plan->num_cta_tiles) : plan->grid;
+  info->cta_threads = gen2 ? m2.threads : plan->cta_threads;
   info->launches_per_spmv = plan->launches;
-  info->smem_bytes = plan->smem_bytes;
+  info->smem_bytes = gen2 ? m2.smem : plan->smem_bytes;
   info->workspace_bytes = plan->workspace_bytes;
   return LOOPSB_OK;
 }
@@ -861,9 +984,12 @@ int loopsb_spmv_f32(loopsb_plan_t* plan, const float* values,
       probe_scope probe(plan, s);
       const merge_variant& mv = kMergeVariants[plan->variant];
       const bool array_ends = lay.kind == LOOPSB_LAYOUT_CSR;
-      mv.launch(array_ends, plan->grid, plan->smem_bytes, s, array_ends ? lay.offsets + 1 : nullptr,
-                lay.pitch, col_indices, values, x, y, plan->coords, int(plan->M), T, A, nct,
-                plan->carry_row, plan->carry_val, plan->phases);
+      if (plan->gen == 2 && !plan->phases && aligned16(col_indices, values))
+        launch_merge2(plan, array_ends, false, s, col_indices, values, x, y, num_cols);
+      else
+        mv.launch(array_ends, plan->grid, plan->smem_bytes, s, array_ends ? lay.offsets + 1 : nullptr,
+                  lay.pitch, col_indices, values, x, y, plan->coords, int(plan->M), T, A, nct,
+                  plan->carry_row, plan->carry_val, plan->phases);
       probe.close();
       LOOPSB_CUDA_TRY(cudaGetLastError());
       mp::spmv_merge_fixup_kernel<<<(nct + 255) / 256, 256, 0, s>>>(
@@ -921,8 +1047,11 @@ int loopsb_spmv_f32(loopsb_plan_t* plan, const float* values,
       const merge_variant& mv = kMergeVariants[plan->variant];
       l2_pin_scope pin(plan, x, size_t(num_cols) * sizeof(float), s);
       probe_scope probe(plan, s);
-      mv.launch(true, plan->grid, plan->smem_bytes, s, lay.offsets + 1, 0, col_indices, values, x, y,
-                plan->coords, int(plan->M), T, A, nct, plan->carry_row, plan->carry_val, nullptr);
+      if (plan->gen == 2 && aligned16(col_indices, values))
+        launch_merge2(plan, true, false, s, col_indices, values, x, y, num_cols);
+      else
+        mv.launch(true, plan->grid, plan->smem_bytes, s, lay.offsets + 1, 0, col_indices, values, x, y,
+                  plan->coords, int(plan->M), T, A, nct, plan->carry_row, plan->carry_val, nullptr);
       probe.close();
       LOOPSB_CUDA_TRY(cudaGetLastError());
       mp::spmv_merge_fixup_kernel<<<(nct + 255) / 256, 256, 0, s>>>(plan->carry_row, plan->carry_val, nct, T, y);

@@ -267,10 +267,17 @@ __global__ void __launch_bounds__(THREADS, MINB)
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int cols[4] = {ci[u].x, ci[u].y, ci[u].z, ci[u].w};
+          const int cq = u * THREADS + t;
+          const int pq = (cq < nchunks ? 4 * cq : -8) - skew;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            if (ARRAY_ENDS) xv[u][q] = __ldg(x + cols[q]);
-            else xv[u][q] = cols[q] >= 0 ? __ldg(x + cols[q]) : 0.0f;
+            // words outside the tile's atoms (alignment slack in front of the first
+            // atom, the tail of the last chunk) may be anything when the caller's
+            // arrays are views that do not start on a 16-byte boundary: never
+            // gather through them
+            const int col = unsigned(pq + q) < una ? cols[q] : 0;
+            if (ARRAY_ENDS) xv[u][q] = __ldg(x + col);
+            else xv[u][q] = col >= 0 ? __ldg(x + col) : 0.0f;
           }
         }
       }

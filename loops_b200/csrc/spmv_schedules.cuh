@@ -77,15 +77,21 @@ __global__ void __launch_bounds__(128)
 }
 
 // ------------------------------------------------------------------- group --
-// Sum `v` over runs of equal `key` among consecutive lanes; the first lane of
-// each run ends up with the run total.
+// Sum `v` over runs of equal `key` among CONSECUTIVE lanes; the first lane of
+// each run ends up with the run total. A run ends where the key changes: keys
+// need not be sorted (COO triples arrive in file order), so an equal key further
+// up the warp with a different one in between starts a new run -- the sum is a
+// true segmented one, bounded by the next run head (ballot), not by key equality.
 __device__ __forceinline__ float warp_run_sum(float v, int key, unsigned mask) {
   const int lane = threadIdx.x & 31;
+  const int prev = __shfl_up_sync(mask, key, 1);
+  const unsigned heads = __ballot_sync(mask, lane == 0 || prev != key);
+  const unsigned above = lane == 31 ? 0u : heads & (0xfffffffeu << lane);
+  const int stop = above ? __ffs(above) - 1 : 32;     // first lane of the next run
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const float ov = __shfl_down_sync(mask, v, d);
-    const int ok = __shfl_down_sync(mask, key, d);
-    if (lane + d < 32 && ok == key) v += ov;
+    if (lane + d < stop) v += ov;
   }
   return v;
 }

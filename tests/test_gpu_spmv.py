@@ -343,3 +343,41 @@ def test_automatic_picks_a_schedule_and_matches_the_oracle(oracle):
     y = torch.full((rows,), float("nan"), device="cuda")
     spmv.automatic(B, torch.as_tensor(x).cuda(), y)
     np.testing.assert_array_equal(y.cpu().numpy(), oracle.spmv(off, idx, val, x))
+
+
+def test_coo_unsorted_rows(oracle, tmp_path):
+    """COO triples are not row-sorted in general -- the loader
+    returns file order and mirrors symmetric entries in place. Rows [5,3,5]: the two
+    5s are separate runs; the reference adds every nonzero atomically and accepts
+    any order (coo_thread_mapped.cuh:37-51)."""
+    from loops_b200 import coo_t
+    from loops_b200 import market
+    from loops_b200.algorithms import spmv
+    # the advisor's minimal case
+    r = np.array([5, 3, 5], np.int32); c = np.array([0, 1, 2], np.int32)
+    v = np.array([1.0, 10.0, 100.0], np.float32)
+    y = torch.full((8,), float("nan"), device="cuda")
+    spmv.coo_thread_mapped(coo_t(8, 3, r, c, v), torch.ones(3, device="cuda"), y)
+    np.testing.assert_array_equal(y.cpu().numpy(), np.array([0, 0, 0, 10, 0, 101, 0, 0], np.float32))
+    # a permuted COO of a random matrix, exact inputs
+    off, idx, val = random_csr(700, 500, 0.03, seed=31, exact=True)
+    x = np.random.default_rng(2).integers(1, 11, 500).astype(np.float32)
+    rows_of = np.repeat(np.arange(700, dtype=np.int32), np.diff(off))
+    for seed in (0, 1):
+        perm = np.random.default_rng(seed).permutation(len(idx))
+        if seed == 1:      # short runs of equal rows separated by other rows
+            perm = np.argsort(rows_of % 7, kind="stable")
+        y = torch.full((700,), float("nan"), device="cuda")
+        spmv.coo_thread_mapped(coo_t(700, 500, rows_of[perm], idx[perm], val[perm]), torch.as_tensor(x).cuda(), y)
+        np.testing.assert_array_equal(y.cpu().numpy(), oracle.spmv(off, idx, val, x))
+    # a symmetric .mtx loaded straight to COO (mirrors sit right after their sources)
+    p = tmp_path / "sym.mtx"
+    ent = [(i + 1, j + 1, (i * 7 + j) % 16 / 8 + 0.125) for i in range(60) for j in range(0, i + 1, 3)]
+    p.write_text("%%MatrixMarket matrix coordinate real symmetric\n" + "60 60 %d\n" % len(ent) +
+                 "".join("%d %d %.3f\n" % e for e in ent))
+    rows, cols, rr, cc, vv = market.load_coo(str(p))
+    xs = np.random.default_rng(5).integers(1, 11, cols).astype(np.float32)
+    y = torch.full((rows,), float("nan"), device="cuda")
+    spmv.coo_thread_mapped(coo_t(rows, cols, rr, cc, vv), torch.as_tensor(xs).cuda(), y)
+    o2, i2, v2 = market.coo_to_csr(rows, cols, rr, cc, vv)
+    np.testing.assert_array_equal(y.cpu().numpy(), oracle.spmv(o2, i2, v2, xs))
