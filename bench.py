@@ -9,8 +9,9 @@ A "step" is one SpMV  y = A x  over the whole matrix.
            2^25 nnz, fp32, merge_path_flat, one B200.
   N  > 1 : BASELINE.json configs[4] -- 2^24 rows / 2^29 nnz row-partitioned over
            the N ranks (contiguous row ranges, global column ids); every step is
-           one NCCL all-gather of the dense x shards followed by the local
-           merge-path SpMV. Total work is fixed as N grows ("strong").
+           loopsb_dist_spmv (C ABI, loops_b200/csrc/dist.cu): the NCCL all-gather of
+           the dense x shards, phased so that it overlaps the local merge-path SpMV
+           of the shard's column blocks. Total work is fixed as N grows ("strong").
 Inputs are generated in HBM (deterministic counter-based generator, x = the
 reference's recipe) and exceed the 126 MB L2 (272 MB of matrix per step), so
 consecutive timed steps cannot be served from cache ("l2": "inputs_exceed_l2").
@@ -196,26 +197,27 @@ def run_reference_arm(args, rank, world):
     emit(line)
 
 
-def dist_overlap_enabled(n):
-    return n > 1 and os.environ.get("LOOPSB_DIST_OVERLAP", "0") == "1"
-
-
-def workload_config(n):
-    overlap = dist_overlap_enabled(n)
+def workload_config(n, groups=None):
     if n == 1:
         return {"workload": "synthetic power-law CSR 2^20 rows / 2^25 nnz fp32, merge_path_flat (BASELINE configs[1])",
                 "rows": CFG2["rows"], "nnz": CFG2["nnz"], "schedule": "merge_path_flat", "layout": "csr",
                 "degree_law": "P(d)~d^-2.1, d in [1,1024], seeded row order", "columns": "stratified hash, unique ascending",
                 "l2": "inputs_exceed_l2", "partition": "none"}
+    if groups is None:
+        from loops_b200.dist import default_groups
+        groups = default_groups(n)
     return {"workload": "synthetic power-law CSR 2^24 rows / 2^29 nnz fp32, merge_path_flat, row-partitioned, "
-                        "one NCCL all-gather of x per step (BASELINE configs[4])",
+                        "NCCL all-gather of x per step (BASELINE configs[4])",
             "rows": CFG5["rows"], "nnz": CFG5["nnz"], "schedule": "merge_path_flat", "layout": "csr",
-            "l2": "inputs_exceed_l2", "partition": f"row{n}", "collective": "nccl all_gather(x)",
-            "overlap": ("own-column part of the shard runs during the all-gather (LOOPSB_DIST_OVERLAP=1)"
-                        if overlap else "none (all-gather, then one SpMV)"),
+            "l2": "inputs_exceed_l2", "partition": f"row{n}",
+            "collective": ("nccl all-gather of x issued as ring-shifted send/recv phases " + str(groups) +
+                           " (chunks per phase) overlapping the SpMV of the shard's column blocks"
+                           if groups else "one ncclAllGather(x), then one SpMV"),
+            "api": "loopsb_dist_spmv (C ABI; NCCL driven by libloopsb200.so)",
             "note": "N>1 runs BASELINE configs[4], 16x the N=1 workload (configs[1]): total work is fixed across "
                     "N=2/4/8 (strong scaling among them), but it is NOT the N=1 matrix -- its x is 64 MB, so the "
-                    "band-tiled plan's cost model declines and every shard runs the plain CSR merge-path kernel"}
+                    "band-tiled plan's cost model declines and every shard runs the CSR merge-path kernel; "
+                    "`single_gpu_same_workload` gives this workload on one GPU"}
 
 
 def emit(line: dict):
@@ -236,6 +238,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-same-workload", action="store_true",
+                    help="N > 1: skip timing the whole configs[4] matrix on rank 0's GPU alone")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -284,38 +288,25 @@ def main():
     tiled = plan.tiled_info()            # None when the cost model kept the plain CSR kernel
     launches_per_spmv = 1 if tiled else int(info.launches_per_spmv)
 
-    # N > 1: the shard is split by column range so that the part that only needs the
-    # rank's OWN x shard runs while the all-gather is in flight (still one collective
-    # per step): y = A_own @ x_shard + A_rest @ allgather(x). Opt-in (LOOPSB_DIST_OVERLAP=1):
-    # measured at N=2 it hides the all-gather but the two sparser SpMVs cost as much more
-    # (1.588 vs 1.599 ms per step, kernels 1.70 vs 1.49 ms), so the default stays
-    # all-gather -> one SpMV.
-    overlap = dist_overlap_enabled(N)
-    A_own = A_rest = y_own = plan_rest = plan_own = None
-    if overlap:
-        from loops_b200.dist import split_columns
-        c0, c1 = (cols * rank) // N, (cols * (rank + 1)) // N
-        (o_off, o_idx, o_val), (q_off, q_idx, q_val) = split_columns(off, idx, val, c0, c1)
-        A_own = csr_t.from_tensors(r1 - r0, c1 - c0, o_off, o_idx, o_val)
-        A_rest = csr_t.from_tensors(r1 - r0, cols, q_off, q_idx, q_val)
-        y_own = torch.empty_like(y)
-        plan_own = A_own.plan(_lib.SCHED_MERGE_PATH_FLAT, stream)
-        plan_rest = A_rest.plan(_lib.SCHED_MERGE_PATH_FLAT, stream)
-        launches_per_spmv = (1 if plan_own.tiled_info() else int(plan_own.info().launches_per_spmv)) + \
-                            (1 if plan_rest.tiled_info() else int(plan_rest.info().launches_per_spmv)) + 1
+    # N > 1: the whole step is loopsb_dist_spmv (C ABI). torch.distributed only hands
+    # rank 0's NCCL id to the other ranks and reduces the timings.
+    dp = None
+    groups = []
+    if N > 1:
+        from loops_b200.dist import DistPlan, default_groups
+        groups = default_groups(N)
+        t_dp = time.perf_counter()
+        dp = DistPlan.from_process_group(A, groups=groups, stream=stream)
         torch.cuda.synchronize()
+        plan_s += time.perf_counter() - t_dp
+        dinfo = dp.info()
+        launches_per_spmv = 2 * dinfo["num_blocks"] + (len(groups) if groups else 1)
 
     def step():
-        if overlap:
-            work = dist.all_gather_into_tensor(x_full, x_shard, async_op=True)
-            spmv.merge_path_flat(A_own, x_shard, y_own, stream=stream, sync=False)
-            work.wait()                                   # the launching stream now waits for the collective
-            spmv.merge_path_flat(A_rest, x_full, y, stream=stream, sync=False)
-            y.add_(y_own)
-            return
         if N > 1:
-            dist.all_gather_into_tensor(x_full, x_shard)
-        spmv.merge_path_flat(A, x_full, y, stream=stream, sync=False)
+            dp(x_shard, y, stream)
+        else:
+            spmv.merge_path_flat(A, x_full, y, stream=stream, sync=False)
 
     def barrier():
         if N > 1:
@@ -344,17 +335,36 @@ def main():
     value = nnz / (ms_step * 1e-3)
 
     # ---- kernel-only probes (second pass; not part of `value`) ----
-    if overlap:
-        plan_own.probe_begin(args.steps)
-        plan_rest.probe_begin(args.steps)
+    breakdown = None
+    if N > 1:
+        # per step: CUDA events around the all-gather (first send/recv issued -> last chunk
+        # landed) and around every column block's SpMV; one step at a time (probe_read syncs)
+        dp.probe(True)
+        reads = []
+        for _ in range(min(args.steps, 20)):
+            barrier()
+            step()
+            reads.append(dp.probe_read())
+        dp.probe(False)
+        kernel_ms = np.array([r["kernel_ms"] for r in reads], np.float32)
+        comm = torch.tensor([float(np.mean([r["comm_ms"] for r in reads])), float(np.mean(kernel_ms))], device=dev)
+        cmax = comm.clone(); dist.all_reduce(cmax, op=dist.ReduceOp.MAX)
+        csum = comm.clone(); dist.all_reduce(csum, op=dist.ReduceOp.SUM)
+        breakdown = {"comm_ms": float(cmax[0].item()), "kernel_ms": float(cmax[1].item()),
+                     "comm_ms_mean_over_ranks": float(csum[0].item()) / N,
+                     "kernel_ms_mean_over_ranks": float(csum[1].item()) / N,
+                     "block_ms_rank0": [float(v) for v in np.mean([r["block_ms"] for r in reads], axis=0)],
+                     "block_nnz_rank0": dinfo["block_nnz"], "groups": groups,
+                     "x_bytes_received_per_rank": int(cols * 4 * (N - 1) // N),
+                     "allgather_GBps_in": cols * 4 * (N - 1) / N / (float(cmax[0].item()) * 1e-3) / 1e9,
+                     "how": "max over ranks of the per-rank means of 20 single steps with probes on: comm = first "
+                            "send/recv issued -> last chunk landed (side stream), kernel = sum of the column "
+                            "blocks' SpMV launches; with phases the two overlap, so comm + kernel > step"}
     else:
         plan.probe_begin(args.steps)
-    for _ in range(args.steps):
-        step()
-    torch.cuda.synchronize()
-    if overlap:   # the local SpMV is two launches of the same kernel (own columns, the rest)
-        kernel_ms = plan_own.probe_collect(args.steps) + plan_rest.probe_collect(args.steps)
-    else:
+        for _ in range(args.steps):
+            step()
+        torch.cuda.synchronize()
         kernel_ms = plan.probe_collect(args.steps)
     local_nnz = int(idx.numel())
     local_bytes = algorithmic_bytes(r1 - r0, cols, local_nnz)
@@ -373,7 +383,8 @@ def main():
                 "traffic": None, "peak_source": peak_src,
                 "kernel": (f"spmv_bt_kernel (band-tiled; CTA {tiled['cta_threads']} thr, grid {tiled['grid_blocks']}, "
                            f"smem {tiled['smem_bytes']} B)" if tiled else
-                           f"spmv_merge_kernel (CTA {info.cta_threads} thr, grid {info.grid_blocks}, smem {info.smem_bytes} B)"),
+                           f"spmv_merge2_kernel (CTA {info.cta_threads} thr, grid {info.grid_blocks}, smem {info.smem_bytes} B"
+                           + (f"; {dinfo['num_blocks']} column blocks per step" if N > 1 else "") + ")"),
                 "kernel_ms_mean": k_ms, "duration_source": k_src,
                 "kernel_ms_event_pair_mean": k_pair_ms, "kernel_ms_event_pair_min": float(np.min(kernel_ms)),
                 "frac_event_pair": local_bytes / (k_pair_ms * 1e-3) / 1e9 / peak,
@@ -419,8 +430,9 @@ def main():
     def e2e_serial_step():
         x_src.copy_(x_host, non_blocking=True)
         if N > 1:
-            dist.all_gather_into_tensor(x_full, x_shard)
-        spmv.merge_path_flat(A, x_full, y, stream=stream, sync=False)
+            dp(x_shard, y, stream)
+        else:
+            spmv.merge_path_flat(A, x_full, y, stream=stream, sync=False)
         y_host[0].copy_(y, non_blocking=True)
 
     def timed(fn_loop):
@@ -441,7 +453,6 @@ def main():
 
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     xd = [x_src.clone() for _ in range(NBUF)]
-    xf = [x_full] + [x_full.clone() for _ in range(NBUF - 1)] if N > 1 else xd
     yd = [y] + [y.clone() for _ in range(NBUF - 1)]
     ev_in = [torch.cuda.Event() for _ in range(NBUF)]
     ev_done = [torch.cuda.Event() for _ in range(NBUF)]
@@ -459,8 +470,9 @@ def main():
             stream.wait_event(ev_in[b])
             stream.wait_event(ev_out[b])              # yd[b] has been drained to the host
             if N > 1:
-                dist.all_gather_into_tensor(xf[b], xd[b])
-            spmv.merge_path_flat(A, xf[b], yd[b], stream=stream, sync=False)
+                dp(xd[b], yd[b], stream)
+            else:
+                spmv.merge_path_flat(A, xd[b], yd[b], stream=stream, sync=False)
             ev_done[b].record(stream)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_done[b])
@@ -537,6 +549,8 @@ def main():
     y_e2e_ok = bool(torch.equal(torch.from_numpy(y_host[(args.steps - 1) % NBUF].numpy()).to(dev), yd[(args.steps - 1) % NBUF]))
 
     # correctness guard on the timed configuration (exact inputs -> exact sums)
+    step()
+    torch.cuda.synchronize()
     chk = float(y.double().sum().item())
 
     cpu = None
@@ -549,12 +563,71 @@ def main():
                "host_cores_available": os.cpu_count(),
                "y_matches_gpu_bit_exact": bool(np.array_equal(y_cpu, y.cpu().numpy()))}
 
+    # ---- N > 1: parity on the hardware that ran the timed steps ----
+    #  * every rank: the first 2^16 rows of its y shard against the reference's CPU SpMV
+    #    (the cpu_baseline leg's library) on the same rows, bit for bit;
+    #  * globally: sum(y) over all ranks (fp64; every term is a multiple of 1/8, so the sum
+    #    is exact) against sum_j x_j * (column sum_j of A), formed with torch ops only.
+    dist_check = None
+    same_workload = None
+    if N > 1:
+        prefix = min(1 << 16, r1 - r0)
+        pn = int(off[prefix].item())
+        o, i_, v = off[: prefix + 1].cpu().numpy(), idx[:pn].cpu().numpy(), val[:pn].cpu().numpy()
+        xx = x_full.cpu().numpy()
+        _, kind, y_cpu = cpu_spmv_seconds(o, i_, v, xx, prefix, cols, 1, 1)
+        ok_prefix = bool(np.array_equal(y_cpu, y[:prefix].cpu().numpy()))
+        colsum = torch.zeros(cols, dtype=torch.float64, device=dev).index_add_(0, idx.long(), val.double())
+        sums = torch.stack([y.double().sum(), (colsum * x_full.double()).sum(),
+                            torch.tensor(0.0 if ok_prefix else 1.0, dtype=torch.float64, device=dev)])
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        gathered_ok = bool(torch.equal(dp.x_full(cols), x_full))
+        flag = torch.tensor([0.0 if gathered_ok else 1.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.SUM)
+        dist_check = {"y_matches_oracle": bool(sums[2].item() == 0.0 and sums[0].item() == sums[1].item()),
+                      "prefix_rows_per_rank": prefix, "prefix_checker": kind, "ranks_with_prefix_mismatch": int(sums[2].item()),
+                      "global_checksum": float(sums[0].item()), "global_checksum_expected": float(sums[1].item()),
+                      "gathered_x_equals_x_on_all_ranks": bool(flag.item() == 0.0)}
+        del colsum
+        # the same workload on ONE GPU (rank 0, after the timed region): the whole 2^24 x 2^29
+        # matrix generated in 8 row slices, plain merge-path kernel (what loopsb_spmv_f32 runs
+        # for it; x = 64 MB does not fit the band-tiled plan)
+        if rank == 0 and not args.no_same_workload:
+            try:
+                offs, idxs, vals = [], [], []
+                base = 0
+                for sl in range(8):
+                    a0, a1 = rows * sl // 8, rows * (sl + 1) // 8
+                    o_, i__, v_ = g.synth_csr(rows, cols, nnz, device=dev, degrees=deg, row_begin=a0, row_end=a1)
+                    offs.append(o_[:-1].long() + base if sl < 7 else o_.long() + base)
+                    base += int(o_[-1].item())
+                    idxs.append(i__); vals.append(v_)
+                Afull = csr_t.from_tensors(rows, cols, torch.cat(offs).to(torch.int32), torch.cat(idxs), torch.cat(vals))
+                del offs, idxs, vals
+                yf = torch.empty(rows, dtype=torch.float32, device=dev)
+                for _ in range(3):
+                    spmv.merge_path_flat(Afull, x_full, yf, stream=stream, sync=False, tiled=False)
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record(stream)
+                for _ in range(10):
+                    spmv.merge_path_flat(Afull, x_full, yf, stream=stream, sync=False, tiled=False)
+                b_.record(stream); b_.synchronize()
+                ms1 = a_.elapsed_time(b_) / 10
+                same_workload = {"value": nnz / (ms1 * 1e-3), "unit": UNIT, "ms_per_step": ms1, "n_gpus": 1,
+                                 "y_checksum": float(yf.double().sum().item()),
+                                 "how": "rank 0, after the timed region: whole configs[4] matrix resident on one "
+                                        "B200, 10 back-to-back merge_path_flat SpMVs, CUDA events"}
+                del Afull, yf
+            except Exception as e:          # out of memory on a shared box: report, do not fail the bench
+                same_workload = {"error": repr(e)[:200]}
+        dist.barrier()
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(N), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "config": workload_config(N, groups), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches_per_spmv * args.steps,
             "clocks": clocks.report(),
             "plan": {"grid_blocks": info.grid_blocks, "cta_threads": info.cta_threads,
@@ -563,8 +636,17 @@ def main():
                      "kernel": "band-tiled (plan-owned re-ordered copy of the matrix)" if tiled else "csr merge-path"},
             "y_checksum": chk, "e2e_y_equal_device_y": y_e2e_ok,
         }
+        if N > 1:
+            line["comm_ms"] = breakdown["comm_ms"]
+            line["kernel_ms"] = breakdown["kernel_ms"]
+            line["breakdown"] = breakdown
+            line["y_matches_oracle"] = dist_check["y_matches_oracle"]
+            line["dist_check"] = dist_check
+            line["single_gpu_same_workload"] = same_workload
+            line["dist"] = dinfo
         emit(line)
     if N > 1:
+        dp.close()
         dist.destroy_process_group()
 
 

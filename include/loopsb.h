@@ -110,6 +110,10 @@ int loopsb_plan_create(loopsb_plan_t** out, const loopsb_layout_t* lay,
                        int schedule, void* stream);
 int loopsb_plan_destroy(loopsb_plan_t* plan);
 int loopsb_plan_info(const loopsb_plan_t* plan, loopsb_plan_info_t* info);
+/* Tuning hint: the number of bytes of x the matrix's columns range over when that is
+ * less than num_cols * sizeof(value) (a column block of a larger matrix). Only the launch
+ * geometry depends on it (resident CTAs per SM vs L1 capacity), never the result. */
+int loopsb_plan_hint_x_bytes(loopsb_plan_t* plan, int64_t bytes);
 /* Copy the merge-path tile start coordinates S(b * TPB*IPT), b = 0..M, to a
  * HOST array of 2*(M+1) int32 (x0,y0,x1,y1,...). Synchronises. This is what
  * the reference's generate_search_coordinates (merge_path_flat.hxx:45-76)
@@ -158,6 +162,13 @@ int loopsb_spmv_f32(loopsb_plan_t* plan, const float* values,
                     const int32_t* col_indices, const int32_t* row_indices,
                     const float* x, float* y, int32_t num_rows,
                     int32_t num_cols, void* stream);
+
+/* y += A x for a merge_path_flat plan over CSR (same kernel, read-modify-write of the
+ * rows it closes; deterministic). Used for the second and later column blocks of a
+ * multi-GPU shard (loopsb_dist_*). LOOPSB_ERR_UNSUPPORTED for other plans or for
+ * indices / values that are not 16-byte aligned. */
+int loopsb_spmv_acc_f32(loopsb_plan_t* plan, const float* values, const int32_t* col_indices,
+                        const float* x, float* y, int32_t num_rows, int32_t num_cols, void* stream);
 
 /* BCSR R x C dense blocks (values[b*R*C + i*C + j], container/bcsr.hxx:14-22),
  * one thread per block-row, fp32 FMA. Replaces
@@ -368,6 +379,83 @@ int loopsb_csr_to_dia_fill(int32_t num_rows, int32_t num_cols, int64_t nnz,
                            const int32_t* offsets, const int32_t* indices, const float* values,
                            int32_t num_diagonals, int32_t* diag_offsets, float* dia_values,
                            void* stream);
+
+/* Column-block split of a CSR matrix (the multi-GPU shards of SURVEY.md section 8e): the
+ * columns are cut into `num_chunks` equal ranges of `chunk_cols` (one per source rank of
+ * the x all-gather) and host_block_of_chunk[c] in [0, num_blocks) names the output block
+ * the entries of chunk c go to. count: block_offsets[num_blocks * (num_rows + 1)] = every
+ * block's own CSR offsets (each starting at 0), host_block_nnz[num_blocks] (HOST). fill:
+ * out_indices / out_values [nnz + 4 * num_blocks] = the blocks one after the other, each
+ * starting on a 16-byte boundary (start_0 = 0, start_b = round_up(start_{b-1} + nnz_{b-1}, 4)),
+ * CSR order kept inside every block, column ids stay GLOBAL. */
+int loopsb_csr_split_columns_count(int32_t num_rows, int64_t nnz, const int32_t* offsets,
+                                   const int32_t* indices, int32_t chunk_cols, int32_t num_chunks,
+                                   const int32_t* host_block_of_chunk, int32_t num_blocks,
+                                   int32_t* block_offsets, int64_t* host_block_nnz, void* stream);
+int loopsb_csr_split_columns_fill(int32_t num_rows, int64_t nnz, const int32_t* offsets,
+                                  const int32_t* indices, const float* values, int32_t chunk_cols,
+                                  int32_t num_chunks, const int32_t* host_block_of_chunk,
+                                  int32_t num_blocks, const int32_t* block_offsets,
+                                  const int64_t* host_block_nnz, int32_t* out_indices,
+                                  float* out_values, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Row-partitioned multi-GPU SpMV (BASELINE configs[4]).
+ * The reference is single-GPU (memory.hxx:24 mentions multi-GPU only as a TODO); this
+ * is the north star's design: rank r owns a contiguous row range with GLOBAL column
+ * ids and an equal shard of x (num_cols % world == 0); the only thing that crosses
+ * GPUs is the dense x, all-gathered with NCCL over NVLink. One process (or host
+ * thread) per GPU, the current CUDA device is the rank's GPU. NCCL is loaded with
+ * dlopen("libnccl.so.2") (LOOPSB_NCCL_LIB overrides), so libloopsb200.so does not link it.
+ *
+ *   loopsb_dist_unique_id : rank 0 makes the 128-byte NCCL id; the host launcher hands
+ *                           it to every rank (MPI / torch.distributed / a file).
+ *   loopsb_dist_create    : collective. `groups` = NULL/0: every step is ONE
+ *                           ncclAllGather on the caller's stream followed by one
+ *                           merge-path SpMV over the caller's arrays (borrowed).
+ *                           groups = {g1, g2, ...} (sum = world - 1): the all-gather is
+ *                           issued as ring-shifted NCCL send/recv phases on a side
+ *                           stream -- phase i brings the next g_i chunks in ring order
+ *                           r+1, r+2, ... -- and the plan keeps the shard as column
+ *                           blocks (own columns, then one block per phase; 8 bytes per
+ *                           nonzero of device memory), so block i's SpMV (y += A_i x)
+ *                           runs while phase i+1 is in flight and gathers from a slice
+ *                           of x that stays L2-resident. Same y on exact inputs. The
+ *                           phases are copy-engine pulls from the peers' CUDA-IPC
+ *                           mapped staging buffers, ordered by stream memory operations
+ *                           (no SM, no host barrier); LOOPSB_DIST_TRANSPORT=nccl keeps
+ *                           them as NCCL send/recv groups (also the automatic fallback).
+ *   loopsb_dist_spmv      : y_shard = A_shard * allgather(x_shard); asynchronous on
+ *                           `stream`; x_shard must stay untouched until the call's work
+ *                           on `stream` has completed. Collective: every rank calls it.
+ * ------------------------------------------------------------------------- */
+typedef struct loopsb_dist loopsb_dist_t;
+#define LOOPSB_DIST_ID_BYTES 128
+typedef struct loopsb_dist_info {
+  int32_t world, rank, local_rows, num_cols, num_blocks, nccl_version;
+  int32_t transport;          /* 0 = one ncclAllGather, 1 = NCCL send/recv phases, 2 = copy-engine pulls over CUDA IPC */
+  int32_t reserved_;
+  int64_t local_nnz;
+  int64_t block_nnz[8];
+  int64_t bytes;              /* device memory held by the object (gathered x, column blocks) */
+} loopsb_dist_info_t;
+int loopsb_dist_unique_id(void* id128);
+int loopsb_dist_create(loopsb_dist_t** out, const void* id128, int32_t world, int32_t rank,
+                       int32_t local_rows, int32_t num_cols, int64_t local_nnz,
+                       const int32_t* offsets, const int32_t* col_indices, const float* values,
+                       const int32_t* groups, int32_t num_groups, void* stream);
+int loopsb_dist_spmv(loopsb_dist_t* dist, const float* x_shard, float* y_shard, void* stream);
+int loopsb_dist_info(const loopsb_dist_t* dist, loopsb_dist_info_t* info);
+/* The gathered x of the last step (device pointer owned by the object). */
+int loopsb_dist_x_full(const loopsb_dist_t* dist, const float** x_full);
+/* Breakdown probes: with probing on, every step records CUDA events around the
+ * all-gather (first send/recv issued -> last chunk landed) and around every block's
+ * SpMV; loopsb_dist_probe_read synchronises the device and returns the LAST step's
+ * comm_ms, the sum of its block kernels and (optionally) each block's ms. */
+int loopsb_dist_probe(loopsb_dist_t* dist, int32_t enable);
+int loopsb_dist_probe_read(loopsb_dist_t* dist, float* comm_ms, float* kernel_ms, float* block_ms,
+                           int32_t capacity);
+int loopsb_dist_destroy(loopsb_dist_t* dist);
 
 /* fp64 CSR SpMV (the reference builds its examples
  * for double too, examples/spmv/CMakeLists.txt:29). thread_mapped is bit-equal to

@@ -71,7 +71,15 @@ class TiledInfo(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class DistInfo(C.Structure):
+    """loopsb_dist_info_t"""
+    _fields_ = [(n, C.c_int32) for n in ("world", "rank", "local_rows", "num_cols", "num_blocks", "nccl_version",
+                                         "transport", "reserved_")] + \
+               [("local_nnz", C.c_int64), ("block_nnz", C.c_int64 * 8), ("bytes", C.c_int64)]
+
+
 TILE_FORCE = 1
+DIST_ID_BYTES = 128
 
 # every symbol include/loopsb.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
@@ -83,6 +91,7 @@ SIGNATURES = {
     "loopsb_plan_create": (C.c_int, [C.POINTER(_P), C.POINTER(LayoutDesc), C.c_int, _P]),
     "loopsb_plan_destroy": (C.c_int, [_P]),
     "loopsb_plan_info": (C.c_int, [_P, C.POINTER(PlanInfo)]),
+    "loopsb_plan_hint_x_bytes": (C.c_int, [_P, C.c_int64]),
     "loopsb_plan_merge_coords_host": (C.c_int, [_P, _P, C.c_int64]),
     "loopsb_plan_debug_phases_host": (C.c_int, [_P, _P, C.c_int64]),
     "loopsb_plan_probe_begin": (C.c_int, [_P, C.c_int32]),
@@ -120,6 +129,21 @@ SIGNATURES = {
                                           C.c_int64, _P, _P, C.c_int32, _P]),
     "loopsb_csr_to_dia_count": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _P, _P, C.POINTER(C.c_int32), _P]),
     "loopsb_csr_to_dia_fill": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, C.c_int32, _P, _P, _P]),
+    "loopsb_csr_split_columns_count": (C.c_int, [C.c_int32, C.c_int64, _P, _P, C.c_int32, C.c_int32, _P, C.c_int32,
+                                                 _P, _P, _P]),
+    "loopsb_csr_split_columns_fill": (C.c_int, [C.c_int32, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, _P,
+                                                C.c_int32, _P, _P, _P, _P, _P]),
+    # y += A x and the row-partitioned multi-GPU path
+    "loopsb_spmv_acc_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "loopsb_dist_unique_id": (C.c_int, [_P]),
+    "loopsb_dist_create": (C.c_int, [C.POINTER(_P), _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
+                                     _P, _P, _P, _P, C.c_int32, _P]),
+    "loopsb_dist_spmv": (C.c_int, [_P, _P, _P, _P]),
+    "loopsb_dist_info": (C.c_int, [_P, C.POINTER(DistInfo)]),
+    "loopsb_dist_x_full": (C.c_int, [_P, C.POINTER(_P)]),
+    "loopsb_dist_probe": (C.c_int, [_P, C.c_int32]),
+    "loopsb_dist_probe_read": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, C.c_int32]),
+    "loopsb_dist_destroy": (C.c_int, [_P]),
 }
 
 _lib = None

@@ -116,3 +116,37 @@ def csr_to_dia(csr: csr_t, stream=None) -> dia_t:
                                           _lib.ptr(csr.values), nd, _lib.ptr(offs), _lib.ptr(vals),
                                           _lib.stream_ptr(stream)), "loopsb_csr_to_dia_fill")
     return dia_t.from_tensors(csr.rows, csr.cols, csr.nnzs, offs, vals)
+
+
+def csr_split_columns(csr: csr_t, chunk_cols: int, block_of_chunk, stream=None) -> list[csr_t]:
+    """Column blocks of a CSR matrix (``loopsb_csr_split_columns_*``): columns are cut into
+    equal chunks of ``chunk_cols`` and ``block_of_chunk[c]`` names the block chunk c goes
+    to. Blocks keep CSR order and GLOBAL column ids and share one allocation, each
+    starting on a 16-byte boundary (what the multi-GPU plan holds per shard)."""
+    import numpy as np
+    _need_cuda(csr)
+    dev = csr.values.device
+    lib = _lib.load()
+    nchunks, nblocks = len(block_of_chunk), int(max(block_of_chunk)) + 1
+    boc = np.ascontiguousarray(block_of_chunk, np.int32)
+    boff = torch.empty(nblocks * (csr.rows + 1), dtype=torch.int32, device=dev)
+    bnnz = np.zeros(nblocks, np.int64)
+    _lib.check(lib.loopsb_csr_split_columns_count(csr.rows, csr.nnzs, _lib.ptr(csr.offsets), _lib.ptr(csr.indices),
+                                                  int(chunk_cols), nchunks, boc.ctypes.data, nblocks, _lib.ptr(boff),
+                                                  bnnz.ctypes.data, _lib.stream_ptr(stream)),
+               "loopsb_csr_split_columns_count")
+    idx = torch.empty(csr.nnzs + 4 * nblocks, dtype=torch.int32, device=dev)
+    val = torch.empty(csr.nnzs + 4 * nblocks, dtype=torch.float32, device=dev)
+    _lib.check(lib.loopsb_csr_split_columns_fill(csr.rows, csr.nnzs, _lib.ptr(csr.offsets), _lib.ptr(csr.indices),
+                                                 _lib.ptr(csr.values), int(chunk_cols), nchunks, boc.ctypes.data,
+                                                 nblocks, _lib.ptr(boff), bnnz.ctypes.data, _lib.ptr(idx),
+                                                 _lib.ptr(val), _lib.stream_ptr(stream)),
+               "loopsb_csr_split_columns_fill")
+    out, base = [], 0
+    for b in range(nblocks):
+        base = (base + 3) & ~3
+        n = int(bnnz[b])
+        out.append(csr_t.from_tensors(csr.rows, csr.cols, boff[b * (csr.rows + 1): (b + 1) * (csr.rows + 1)],
+                                      idx[base: base + n], val[base: base + n]))
+        base += n
+    return out

@@ -208,11 +208,13 @@ int merge2_variant_from_env() {
   int v = atoi(e);
   return (v >= 0 && v < kNumMerge2Variants) ? v : -1;
 }
-// Measured on B200 (profiles/merge_probe_r02.txt): 6 CTAs/SM for config 2 (x = 4 MB,
-// 161 vs 170 us), 4 CTAs/SM for the multi-GPU shards (x = 64 MB, 345 vs 355 us).
+// Measured on B200 (profiles/merge_probe_r02.txt, block_probe_r02.txt): 6 CTAs/SM for config 2
+// (x = 4 MB, 161 vs 170 us) and for the column blocks of a multi-GPU shard (x slices of
+// 8..56 MB: 361 vs 380 us per 1/8 shard), 4 CTAs/SM when the gathers range over all of a
+// 64 MB x at once (345 vs 354 us).
 inline int merge2_pick(int forced, size_t x_bytes) {
   if (forced >= 0) return forced;
-  return x_bytes >= (size_t(32) << 20) ? 2 : 0;
+  return x_bytes >= (size_t(60) << 20) ? 2 : 0;
 }
 }  // namespace
 
@@ -228,6 +230,7 @@ struct loopsb_plan {
   int variant = 0;
   int gen = 1;        // merge kernel generation (2 = spmv_merge2.cuh, needs 16-byte aligned arrays)
   int variant2 = -1;  // index into kMerge2Variants forced by LOOPSB_MERGE2_VARIANT, -1 = pick per call
+  long long x_span_bytes = -1;   // loopsb_plan_hint_x_bytes: how much of x the matrix's columns touch
   int wo_grid = 0;   // work_oriented: reference-style grid (blocks of 128 threads)
   long long* phases = nullptr;  // LOOPSB_DEBUG_PHASES=1: per-CTA phase cycle counters
   int* carry_row = nullptr;
@@ -292,7 +295,8 @@ cudaError_t prepare_merge2(int forced) {
 // Second-generation merge-path launch (merge_path_flat / ell_merge_path / work_oriented tiles).
 void launch_merge2(const loopsb_plan* plan, bool array_ends, bool accumulate, cudaStream_t s,
                    const int32_t* col_indices, const float* values, const float* x, float* y, int32_t num_cols) {
-  const merge2_variant& m2 = kMerge2Variants[merge2_pick(plan->variant2, size_t(num_cols) * sizeof(float))];
+  const size_t x_bytes = plan->x_span_bytes >= 0 ? size_t(plan->x_span_bytes) : size_t(num_cols) * sizeof(float);
+  const merge2_variant& m2 = kMerge2Variants[merge2_pick(plan->variant2, x_bytes)];
   const int grid = std::min(m2.ctas_per_sm * plan->sm_count, plan->num_cta_tiles);
   m2.launch(array_ends, accumulate, grid, m2.smem, s, array_ends ? plan->lay.offsets + 1 : nullptr, plan->lay.pitch,
             col_indices, values, x, y, plan->coords, int(plan->M), plan->lay.num_tiles, plan->lay.num_atoms,
@@ -352,26 +356,45 @@ namespace {
 // (the 64 MB x of the multi-GPU shards) the matrix stream pushes it out of the
 // 126 MB L2 between uses. Pin it for the duration of the launch: persisting-L2
 // access-policy window over x on the launching stream (misses stream through),
-// removed again right after the launch so the caller's stream is left as it was.
+// replaced by the caller's previous window right after the launch, so the stream is left as it was.
 // Measured on the 1/8 shard of BASELINE configs[4]: 430 -> 379 us.
 struct l2_pin_scope {
   cudaStream_t s;
   bool on = false;
+  cudaStreamAttrValue prev{};     // the caller's own window on this stream, restored afterwards
   l2_pin_scope(const loopsb_plan* p, const float* x, size_t bytes, cudaStream_t stream) : s(stream) {
     static const bool off = getenv("LOOPSB_NO_L2_PIN") != nullptr;
     if (off || bytes < (size_t(16) << 20)) return;
-    static int max_persist = -1, max_window = -1;
-    if (max_persist < 0) {
-      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, p->device);
-      cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, p->device);
-      if (max_persist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(max_persist));
-      (void)cudaGetLastError();
+    // limits are per device; the persisting carve-out is raised once per device, under a lock
+    // (several ranks / host threads may make their first call at the same time)
+    static std::mutex mu;
+    static int max_persist[64], max_window[64];
+    static bool known[64];
+    const int dev = p->device;
+    if (dev < 0 || dev >= 64) return;
+    int persist, window;
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      if (!known[dev]) {
+        max_persist[dev] = max_window[dev] = 0;
+        cudaDeviceGetAttribute(&max_persist[dev], cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_window[dev], cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        if (max_persist[dev] > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, size_t(max_persist[dev]));
+        (void)cudaGetLastError();
+        known[dev] = true;
+      }
+      persist = max_persist[dev];
+      window = max_window[dev];
     }
-    if (max_persist <= 0 || max_window <= 0) return;
+    if (persist <= 0 || window <= 0) return;
+    if (cudaStreamGetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &prev) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return;
+    }
     cudaStreamAttrValue v{};
     v.accessPolicyWindow.base_ptr = const_cast<float*>(x);
-    v.accessPolicyWindow.num_bytes = std::min(size_t(max_window), bytes);
-    const double ratio = double(std::min(size_t(max_persist), bytes)) / double(v.accessPolicyWindow.num_bytes);
+    v.accessPolicyWindow.num_bytes = std::min(size_t(window), bytes);
+    const double ratio = double(std::min(size_t(persist), bytes)) / double(v.accessPolicyWindow.num_bytes);
     v.accessPolicyWindow.hitRatio = ratio > 1.0 ? 1.0f : float(ratio);
     v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
@@ -380,9 +403,7 @@ struct l2_pin_scope {
   }
   ~l2_pin_scope() {
     if (!on) return;
-    cudaStreamAttrValue v{};
-    v.accessPolicyWindow.num_bytes = 0;   // no window for what the caller launches next
-    cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v);
+    cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &prev);   // what the caller had (usually none)
     (void)cudaGetLastError();
   }
 };
@@ -874,6 +895,12 @@ int loopsb_plan_create(loopsb_plan_t** out, const loopsb_layout_t* lay,
   return LOOPSB_OK;
 }
 
+int loopsb_plan_hint_x_bytes(loopsb_plan_t* plan, int64_t bytes) {
+  LOOPSB_REQUIRE(plan != nullptr, "plan is null");
+  plan->x_span_bytes = bytes;
+  return LOOPSB_OK;
+}
+
 int loopsb_plan_info(const loopsb_plan_t* plan, loopsb_plan_info_t* info) {
   LOOPSB_REQUIRE(plan != nullptr && info != nullptr, "null argument");
   memset(info, 0, sizeof(*info));
@@ -1062,6 +1089,32 @@ int loopsb_spmv_f32(loopsb_plan_t* plan, const float* values,
       set_error("unknown schedule in plan");
       return LOOPSB_ERR_INVALID;
   }
+}
+
+int loopsb_spmv_acc_f32(loopsb_plan_t* plan, const float* values, const int32_t* col_indices, const float* x,
+                        float* y, int32_t num_rows, int32_t num_cols, void* stream) {
+  LOOPSB_REQUIRE(plan != nullptr, "plan is null");
+  LOOPSB_REQUIRE(num_rows >= 0 && num_cols >= 0, "negative dimensions");
+  LOOPSB_REQUIRE(plan->schedule == LOOPSB_SCHED_MERGE_PATH_FLAT && plan->lay.kind == LOOPSB_LAYOUT_CSR,
+                 "y += A x exists for merge_path_flat plans over CSR");
+  const int T = plan->lay.num_tiles, A = plan->lay.num_atoms;
+  LOOPSB_REQUIRE(T == num_rows, "layout tiles must equal num_rows");
+  if (num_rows == 0 || A == 0) return LOOPSB_OK;
+  LOOPSB_REQUIRE(values && col_indices && x && y, "null matrix / x / y pointer");
+  if (plan->gen != 2 || !aligned16(col_indices, values)) {
+    set_error("y += A x needs the second-generation merge kernel and 16-byte aligned indices / values");
+    return LOOPSB_ERR_UNSUPPORTED;
+  }
+  cudaStream_t s = as_stream(stream);
+  const int nct = plan->num_cta_tiles;
+  l2_pin_scope pin(plan, x, size_t(num_cols) * sizeof(float), s);
+  probe_scope probe(plan, s);
+  launch_merge2(plan, true, true, s, col_indices, values, x, y, num_cols);
+  probe.close();
+  LOOPSB_CUDA_TRY(cudaGetLastError());
+  mp::spmv_merge_fixup_kernel<<<(nct + 255) / 256, 256, 0, s>>>(plan->carry_row, plan->carry_val, nct, T, y);
+  LOOPSB_CUDA_TRY(cudaGetLastError());
+  return LOOPSB_OK;
 }
 
 int loopsb_spmv_bcsr_f32(int32_t R, int32_t C, const loopsb_layout_t* lay,

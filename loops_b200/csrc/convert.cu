@@ -280,6 +280,68 @@ int block_sort(int R, int C, int rows, int cols, int64_t nnz, const int* off, co
 
 }  // namespace
 
+namespace {
+// ---- csr -> column blocks (multi-GPU shards) ----------------------------------
+// Columns are cut into equal chunks (one per source rank of the x all-gather);
+// chunk_block.b[c] names the output block chunk c belongs to. One warp per row;
+// CSR order is kept inside every block, column ids stay global.
+constexpr int kMaxSplitChunks = 64;
+constexpr int kMaxSplitBlocks = 8;
+struct split_map { signed char b[kMaxSplitChunks]; };
+
+__global__ void split_count_kernel(int rows, const int* __restrict__ off, const int* __restrict__ idx,
+                                   int chunk_cols, split_map map, int nblocks, int* __restrict__ counts) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  int cnt[kMaxSplitBlocks];
+#pragma unroll
+  for (int b = 0; b < kMaxSplitBlocks; ++b) cnt[b] = 0;
+  for (int a = off[row] + lane; a < off[row + 1]; a += 32) {
+    const int blk = map.b[idx[a] / chunk_cols];
+#pragma unroll
+    for (int b = 0; b < kMaxSplitBlocks; ++b) cnt[b] += (blk == b);
+  }
+#pragma unroll
+  for (int b = 0; b < kMaxSplitBlocks; ++b) {
+    if (b >= nblocks) break;
+    int v = cnt[b];
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    if (lane == 0) counts[size_t(b) * (rows + 1) + row] = v;
+  }
+}
+
+__global__ void split_fill_kernel(int rows, const int* __restrict__ off, const int* __restrict__ idx,
+                                  const float* __restrict__ val, int chunk_cols, split_map map, int nblocks,
+                                  const int* __restrict__ block_off, const long long* __restrict__ block_base,
+                                  int* __restrict__ out_idx, float* __restrict__ out_val) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  long long pos[kMaxSplitBlocks];
+#pragma unroll
+  for (int b = 0; b < kMaxSplitBlocks; ++b)
+    pos[b] = b < nblocks ? block_base[b] + block_off[size_t(b) * (rows + 1) + row] : 0;
+  const int end = off[row + 1];
+  for (int base = off[row]; base < end; base += 32) {
+    const int a = base + lane;
+    const bool live = a < end;
+    int col = 0, blk = -1;
+    float v = 0.0f;
+    if (live) { col = idx[a]; v = val[a]; blk = map.b[col / chunk_cols]; }
+    long long dst = -1;
+#pragma unroll
+    for (int b = 0; b < kMaxSplitBlocks; ++b) {
+      if (b >= nblocks) break;
+      const unsigned m = __ballot_sync(0xffffffffu, blk == b);
+      if (blk == b) dst = pos[b] + __popc(m & ((1u << lane) - 1u));
+      pos[b] += __popc(m);
+    }
+    if (live) { out_idx[dst] = col; out_val[dst] = v; }
+  }
+}
+}  // namespace
+
 extern "C" {
 
 int loopsb_csr_to_coo(int32_t num_rows, int64_t nnz, const int32_t* offsets, int32_t* row_indices, void* stream) {
@@ -469,6 +531,85 @@ int loopsb_csr_to_dia_fill(int32_t num_rows, int32_t num_cols, int64_t nnz, cons
   LOOPSB_CUDA_TRY(cudaMemsetAsync(dia_values, 0, size_t(nd) * size_t(num_rows) * 4, s));
   dia_fill_kernel<<<blocks_for(nnz), kThreads, 0, s>>>(nnz, num_rows, num_cols, rowid.as<int>(), indices, values,
                                                         pos.as<int>(), dia_values);
+  LOOPSB_CUDA_TRY(cudaGetLastError());
+  LOOPSB_CUDA_TRY(cudaStreamSynchronize(s));
+  return LOOPSB_OK;
+}
+
+namespace {
+int split_map_from(const int32_t* host_block_of_chunk, int32_t num_chunks, int32_t num_blocks, split_map* m) {
+  LOOPSB_REQUIRE(host_block_of_chunk != nullptr, "null argument");
+  LOOPSB_REQUIRE(num_chunks >= 1 && num_chunks <= kMaxSplitChunks, "1..64 column chunks");
+  LOOPSB_REQUIRE(num_blocks >= 1 && num_blocks <= kMaxSplitBlocks, "1..8 column blocks");
+  memset(m, 0, sizeof(*m));
+  for (int c = 0; c < num_chunks; ++c) {
+    LOOPSB_REQUIRE(host_block_of_chunk[c] >= 0 && host_block_of_chunk[c] < num_blocks, "block id out of range");
+    m->b[c] = static_cast<signed char>(host_block_of_chunk[c]);
+  }
+  return LOOPSB_OK;
+}
+}  // namespace
+
+int loopsb_csr_split_columns_count(int32_t num_rows, int64_t nnz, const int32_t* offsets, const int32_t* indices,
+                                   int32_t chunk_cols, int32_t num_chunks, const int32_t* host_block_of_chunk,
+                                   int32_t num_blocks, int32_t* block_offsets, int64_t* host_block_nnz,
+                                   void* stream) {
+  CONV_COMMON_CHECKS(num_rows, chunk_cols, nnz);
+  LOOPSB_REQUIRE(offsets && block_offsets && host_block_nnz && chunk_cols > 0, "null argument");
+  split_map m;
+  if (int st = split_map_from(host_block_of_chunk, num_chunks, num_blocks, &m)) return st;
+  cudaStream_t s = as_stream(stream);
+  const size_t stride = size_t(num_rows) + 1;
+  LOOPSB_CUDA_TRY(cudaMemsetAsync(block_offsets, 0, stride * num_blocks * 4, s));
+  if (nnz > 0 && num_rows > 0) {
+    LOOPSB_REQUIRE(indices != nullptr, "null argument");
+    split_count_kernel<<<blocks_for(int64_t(num_rows) * 32), kThreads, 0, s>>>(num_rows, offsets, indices, chunk_cols, m,
+                                                                              num_blocks, block_offsets);
+    LOOPSB_CUDA_TRY(cudaGetLastError());
+  }
+  size_t bytes = 0;
+  LOOPSB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, bytes, block_offsets, block_offsets, int(stride), s));
+  dbuf tmp;
+  CONV_ALLOC(tmp, bytes);
+  for (int b = 0; b < num_blocks; ++b)
+    LOOPSB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, block_offsets + b * stride, block_offsets + b * stride,
+                                                  int(stride), s));
+  for (int b = 0; b < num_blocks; ++b) {
+    int32_t last = 0;
+    LOOPSB_CUDA_TRY(cudaMemcpyAsync(&last, block_offsets + b * stride + num_rows, 4, cudaMemcpyDeviceToHost, s));
+    LOOPSB_CUDA_TRY(cudaStreamSynchronize(s));
+    host_block_nnz[b] = last;
+  }
+  return LOOPSB_OK;
+}
+
+int loopsb_csr_split_columns_fill(int32_t num_rows, int64_t nnz, const int32_t* offsets, const int32_t* indices,
+                                  const float* values, int32_t chunk_cols, int32_t num_chunks,
+                                  const int32_t* host_block_of_chunk, int32_t num_blocks,
+                                  const int32_t* block_offsets, const int64_t* host_block_nnz,
+                                  int32_t* out_indices, float* out_values, void* stream) {
+  CONV_COMMON_CHECKS(num_rows, chunk_cols, nnz);
+  if (nnz == 0 || num_rows == 0) return LOOPSB_OK;
+  LOOPSB_REQUIRE(offsets && indices && values && block_offsets && host_block_nnz && out_indices && out_values &&
+                     chunk_cols > 0, "null argument");
+  split_map m;
+  if (int st = split_map_from(host_block_of_chunk, num_chunks, num_blocks, &m)) return st;
+  cudaStream_t s = as_stream(stream);
+  long long base[kMaxSplitBlocks] = {0};
+  long long run = 0, sum = 0;
+  for (int b = 0; b < num_blocks; ++b) {
+    run = (run + 3) & ~3LL;            // every block starts on a 16-byte boundary
+    base[b] = run;
+    run += host_block_nnz[b];
+    sum += host_block_nnz[b];
+  }
+  LOOPSB_REQUIRE(sum == nnz, "block sizes do not add up to nnz");
+  dbuf dbase;
+  CONV_ALLOC(dbase, sizeof(base));
+  LOOPSB_CUDA_TRY(cudaMemcpyAsync(dbase.p, base, sizeof(base), cudaMemcpyHostToDevice, s));
+  split_fill_kernel<<<blocks_for(int64_t(num_rows) * 32), kThreads, 0, s>>>(
+      num_rows, offsets, indices, values, chunk_cols, m, num_blocks, block_offsets, dbase.as<long long>(),
+      out_indices, out_values);
   LOOPSB_CUDA_TRY(cudaGetLastError());
   LOOPSB_CUDA_TRY(cudaStreamSynchronize(s));
   return LOOPSB_OK;

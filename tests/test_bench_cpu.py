@@ -21,14 +21,22 @@ def _bench():
 
 def test_workload_config_for_every_n(monkeypatch):
     b = _bench()
-    for overlap in ("0", "1"):
-        monkeypatch.setenv("LOOPSB_DIST_OVERLAP", overlap)
+    for groups_env in (None, "0", "1,1,1,2,2"):
+        if groups_env is None:
+            monkeypatch.delenv("LOOPSB_DIST_GROUPS", raising=False)
+        else:
+            monkeypatch.setenv("LOOPSB_DIST_GROUPS", groups_env)
         for n in (1, 2, 4, 8):
             cfg = b.workload_config(n)
             assert "workload" in cfg and "model" not in cfg
             assert cfg["partition"] == ("none" if n == 1 else f"row{n}")
             json.dumps(cfg)
-    assert b.dist_overlap_enabled(1) is False and b.dist_overlap_enabled(8) is True
+    from loops_b200.dist import default_groups
+    monkeypatch.delenv("LOOPSB_DIST_GROUPS", raising=False)
+    for n in (2, 4, 8):
+        assert sum(default_groups(n)) == n - 1          # the phases cover every remote chunk once
+    monkeypatch.setenv("LOOPSB_DIST_GROUPS", "0")
+    assert default_groups(8) == []                       # one ncclAllGather, no split
 
 
 def test_algorithmic_bytes_match_the_survey():

@@ -95,3 +95,31 @@ def test_row_range_covers_everything():
             cuts = [row_range(rows, r, world) for r in range(world)]
             assert cuts[0][0] == 0 and cuts[-1][1] == rows
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+
+
+def test_ring_blocks_and_column_split(oracle):
+    """Host logic of the phased all-gather (loops_b200/csrc/dist.cu): every rank's block map
+    covers each remote chunk once in ring order, and the column blocks add up to the shard."""
+    from loops_b200 import generate as g
+    from loops_b200.dist import ring_blocks, split_column_blocks, shard_csr
+    for world, groups in ((2, [1]), (4, [1, 2]), (8, [2, 2, 3]), (8, [7])):
+        for rank in range(world):
+            m = ring_blocks(world, rank, groups)
+            assert m[rank] == 0 and sorted(m).count(0) == 1
+            order = [m[(rank + k) % world] for k in range(1, world)]
+            assert order == sorted(order)                       # blocks arrive in ring order
+            assert [order.count(b + 1) for b in range(len(groups))] == groups
+    with pytest.raises(ValueError):
+        ring_blocks(4, 0, [1, 1])
+    rows = cols = 2048
+    off, idx, val = (t.numpy() for t in g.synth_csr(rows, cols, rows * 12))
+    x = g.x_recipe(cols).numpy()
+    world, rank = 4, 1
+    l_off, l_idx, l_val = shard_csr(off, idx, val, rank, world)
+    y = np.zeros(len(l_off) - 1, np.float32)
+    total = 0
+    for b_off, b_idx, b_val in split_column_blocks(l_off, l_idx, l_val, cols // world, ring_blocks(world, rank, [1, 2])):
+        y += oracle.spmv(b_off, b_idx, b_val, x)               # exact inputs: any grouping is exact
+        total += len(b_idx)
+    assert total == len(l_idx)
+    np.testing.assert_array_equal(y, oracle.spmv(l_off, l_idx, l_val, x))
