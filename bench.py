@@ -279,6 +279,10 @@ def main():
     x_full = g.x_recipe(cols, device=dev)
     x_shard = x_full[(cols * rank) // N: (cols * (rank + 1)) // N].clone()
     y = torch.empty(r1 - r0, dtype=torch.float32, device=dev)
+    if N > 1:
+        # a real (non-legacy) stream: loopsb_dist_spmv replays its step as a CUDA graph on it
+        torch.cuda.synchronize()
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     stream = torch.cuda.current_stream()
     t_plan = time.perf_counter()
     plan = A.plan(_lib.SCHED_MERGE_PATH_FLAT, stream)   # preprocess (not timed, as in the reference:
@@ -643,7 +647,7 @@ def main():
             line["y_matches_oracle"] = dist_check["y_matches_oracle"]
             line["dist_check"] = dist_check
             line["single_gpu_same_workload"] = same_workload
-            line["dist"] = dinfo
+            line["dist"] = dp.info()
         emit(line)
     if N > 1:
         dp.close()

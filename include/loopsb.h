@@ -434,7 +434,7 @@ typedef struct loopsb_dist loopsb_dist_t;
 typedef struct loopsb_dist_info {
   int32_t world, rank, local_rows, num_cols, num_blocks, nccl_version;
   int32_t transport;          /* 0 = one ncclAllGather, 1 = NCCL send/recv phases, 2 = copy-engine pulls over CUDA IPC */
-  int32_t reserved_;
+  int32_t graphs_cached;      /* CUDA graphs of whole steps held for replay (0 = steps are enqueued call by call) */
   int64_t local_nnz;
   int64_t block_nnz[8];
   int64_t bytes;              /* device memory held by the object (gathered x, column blocks) */

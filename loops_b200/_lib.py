@@ -74,7 +74,7 @@ class TiledInfo(C.Structure):
 class DistInfo(C.Structure):
     """loopsb_dist_info_t"""
     _fields_ = [(n, C.c_int32) for n in ("world", "rank", "local_rows", "num_cols", "num_blocks", "nccl_version",
-                                         "transport", "reserved_")] + \
+                                         "transport", "graphs_cached")] + \
                [("local_nnz", C.c_int64), ("block_nnz", C.c_int64 * 8), ("bytes", C.c_int64)]
 
 

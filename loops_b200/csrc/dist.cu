@@ -161,19 +161,31 @@ struct loopsb_dist {
   bool probing = false;
   long long bytes = 0;
   // copy-engine transport (see the header comment)
-  struct {
+  struct p2p_state {
     bool on = false;
     char* region = nullptr;              // [stage 0 | stage 1 | flags]
     size_t stage_bytes = 0, flags_off = 0;
     std::vector<char*> peer;             // every rank's region as this process sees it (peer[rank] = region)
     std::vector<char> opened;            // 1 = mapped with cudaIpcOpenMemHandle (closed on destroy)
-    cudaStream_t side[2] = {nullptr, nullptr};
-    cudaEvent_t joined = nullptr;
+    static constexpr int kPull = 7;      // copy streams the pulls are spread over (one per peer up to 8 ranks:
+                                         // an 8 MB pull is ~30 us of mostly latency, 7 in flight fill the link)
+    cudaStream_t side[kPull] = {};
+    cudaStream_t pub = nullptr;          // publishes my shard: stage copy + ready flags
+    cudaEvent_t joined[kPull] = {};
+    cudaEvent_t published = nullptr;
     uint32_t step = 0;
     CUresult (*wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
     CUresult (*write32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+    CUresult (*batch)(CUstream, unsigned int, CUstreamBatchMemOpParams*, unsigned int) = nullptr;
   } p2p;
-  std::vector<cudaEvent_t> landed2;      // second side stream's per-block events
+  std::vector<cudaEvent_t> landed_more;  // per block, per extra pull stream (kPull - 1 each)
+  // a step is ~70 driver calls (flag operations, copies, event edges, launches); with 8 ranks the
+  // host could not issue them as fast as the GPU ran them (0.50 ms per step, whatever the phases).
+  // The whole step is therefore captured ONCE per (x_shard, y_shard, buffer parity) into a CUDA
+  // graph and replayed with one cudaGraphLaunch.
+  struct graph_entry { const float* x; float* y; uint32_t q; cudaGraphExec_t exec; };
+  std::vector<graph_entry> graphs;
+  bool use_graphs = true;
 };
 
 namespace {
@@ -191,14 +203,13 @@ void free_dist(loopsb_dist* d) {
     // acknowledged the pull of the last step it took part in, then unmap and free
     cudaDeviceSynchronize();
     if (d->p2p.on && d->p2p.step > 0) {
-      const uint32_t k = d->p2p.step;
-      const size_t off = d->p2p.flags_off + (size_t(2 * d->world) + size_t(k & 1u) * d->world) * 4;
-      std::vector<uint32_t> acks(size_t(d->world));
+      const size_t off = d->p2p.flags_off + size_t(2 * d->world) * 4;
+      std::vector<uint32_t> acks(size_t(2 * d->world));
       for (int spin = 0; spin < 2000; ++spin) {
         if (cudaMemcpy(acks.data(), d->p2p.region + off, acks.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) break;
         bool all = true;
-        for (int p = 0; p < d->world; ++p)
-          if (p != d->rank && int32_t(acks[size_t(p)] - k) < 0) all = false;
+        for (int i = 0; i < 2 * d->world; ++i)
+          if (i % d->world != d->rank && acks[size_t(i)] != 1u) all = false;
         if (all) break;
         usleep(1000);
       }
@@ -208,8 +219,11 @@ void free_dist(loopsb_dist* d) {
     cudaFree(d->p2p.region);
   }
   for (cudaStream_t st : d->p2p.side) if (st) cudaStreamDestroy(st);
-  if (d->p2p.joined) cudaEventDestroy(d->p2p.joined);
-  for (cudaEvent_t e : d->landed2) if (e) cudaEventDestroy(e);
+  if (d->p2p.pub) cudaStreamDestroy(d->p2p.pub);
+  for (cudaEvent_t e : d->p2p.joined) if (e) cudaEventDestroy(e);
+  if (d->p2p.published) cudaEventDestroy(d->p2p.published);
+  for (cudaEvent_t e : d->landed_more) if (e) cudaEventDestroy(e);
+  for (auto& g : d->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   if (d->comm && nccl()) nccl()->CommDestroy(d->comm);
   if (d->x_full) cudaFree(d->x_full);
   if (d->blk_offsets) cudaFree(d->blk_offsets);
@@ -240,13 +254,22 @@ int setup_p2p(loopsb_dist* d, cudaStream_t s) {
     (void)cudaGetLastError();
     ok = false;
   }
+  void* fb = nullptr;
+  if (cudaGetDriverEntryPoint("cuStreamBatchMemOp", &fb, cudaEnableDefault, &qr) != cudaSuccess) { (void)cudaGetLastError(); fb = nullptr; }
+  P.batch = reinterpret_cast<CUresult (*)(CUstream, unsigned int, CUstreamBatchMemOpParams*, unsigned int)>(fb);
   P.wait32 = reinterpret_cast<CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int)>(fw);
   P.write32 = reinterpret_cast<CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int)>(fr);
   P.stage_bytes = (size_t(d->chunk_cols) * sizeof(float) + 255) & ~size_t(255);
   P.flags_off = 2 * P.stage_bytes;
   const size_t region_bytes = P.flags_off + size_t(4 * W) * 4 + 256;
   if (ok && cudaMalloc(&P.region, region_bytes) != cudaSuccess) { (void)cudaGetLastError(); P.region = nullptr; ok = false; }
-  if (ok && (cudaMemsetAsync(P.region, 0, region_bytes, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)) ok = false;
+  if (ok) {
+    std::vector<uint32_t> init(size_t(4 * W), 0u);
+    for (int i = 2 * W; i < 4 * W; ++i) init[size_t(i)] = 1u;       // pulled[q][p] = 1: both buffers are free
+    if (cudaMemsetAsync(P.region, 0, region_bytes, s) != cudaSuccess ||
+        cudaMemcpyAsync(P.region + P.flags_off, init.data(), init.size() * 4, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) ok = false;
+  }
   // record exchanged per rank: {ipc handle 64 B, pid, device, raw pointer, ok}
   struct rec { cudaIpcMemHandle_t h; long long pid; long long dev; unsigned long long ptr; long long ok; };
   static_assert(sizeof(rec) == 96, "exchange record layout");
@@ -294,9 +317,12 @@ int setup_p2p(loopsb_dist* d, cudaStream_t s) {
   if (ok) {
     for (cudaStream_t& st : P.side)
       if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) ok = false;
-    if (cudaEventCreateWithFlags(&P.joined, cudaEventDisableTiming) != cudaSuccess) ok = false;
-    d->landed2.assign(d->blocks.size(), nullptr);
-    for (cudaEvent_t& e : d->landed2)
+    if (cudaStreamCreateWithFlags(&P.pub, cudaStreamNonBlocking) != cudaSuccess) ok = false;
+    for (cudaEvent_t& e : P.joined)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) ok = false;
+    if (cudaEventCreateWithFlags(&P.published, cudaEventDisableTiming) != cudaSuccess) ok = false;
+    d->landed_more.assign(d->blocks.size() * (P.kPull - 1), nullptr);
+    for (cudaEvent_t& e : d->landed_more)
       if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) ok = false;
     (void)cudaGetLastError();
   }
@@ -314,25 +340,62 @@ int setup_p2p(loopsb_dist* d, cudaStream_t s) {
     }                                                                              \
   } while (0)
 
-// One step's x exchange with the copy engines; on return stream `s` may run block g as soon
-// as it has waited for blocks[g].landed (and landed2[g]).
-int exchange_p2p(loopsb_dist* d, const float* x_shard, cudaStream_t s) {
+// One step's x exchange with the copy engines. Nothing here sits in front of block 0 on the
+// caller's stream `s` except the copy of its own chunk: the flag traffic (a posted write over
+// NVLink per peer) runs on the publish stream, the pulls on kPull copy streams. On return `s`
+// may run block g once it has waited for blocks[g].landed and the block's landed_more events.
+int exchange_p2p(loopsb_dist* d, const float* x_shard, cudaStream_t s, uint32_t q) {
   auto& P = d->p2p;
+  constexpr int K = loopsb_dist::p2p_state::kPull;
   const int W = d->world, me = d->rank;
-  const uint32_t k = ++P.step;
-  const uint32_t q = k & 1u;
   const size_t chunk_b = size_t(d->chunk_cols) * sizeof(float);
+  // Flags are binary semaphores with constant wait / write values, so that a whole step can be
+  // replayed as a CUDA graph:
+  //   ready[q][src]    in the PULLER's region : 1 = rank src's stage[q] is full (src sets, puller clears)
+  //   pulled[q][puller] in the OWNER's region : 1 = puller is done with my stage[q] (puller sets, owner
+  //                                             clears; starts at 1)
   auto ready_at = [&](char* region, int src) { return CUdeviceptr(uintptr_t(region + P.flags_off + (size_t(q) * W + src) * 4)); };
   auto pulled_at = [&](char* region, int puller) { return CUdeviceptr(uintptr_t(region + P.flags_off + (size_t(2 * W) + size_t(q) * W + puller) * 4)); };
-  CUstream cs = reinterpret_cast<CUstream>(s);
-  if (k > 2)
-    for (int p = 0; p < W; ++p)
-      if (p != me) CU_TRY(P.wait32(cs, pulled_at(P.region, p), k - 2, CU_STREAM_WAIT_VALUE_GEQ));
-  LOOPSB_CUDA_TRY(cudaMemcpyAsync(P.region + size_t(q) * P.stage_bytes, x_shard, chunk_b, cudaMemcpyDeviceToDevice, s));
-  LOOPSB_CUDA_TRY(cudaMemcpyAsync(d->x_full + size_t(me) * d->chunk_cols, x_shard, chunk_b, cudaMemcpyDeviceToDevice, s));
-  for (int p = 0; p < W; ++p)
-    if (p != me) CU_TRY(P.write32(cs, ready_at(P.peer[size_t(p)], me), k, CU_STREAM_WRITE_VALUE_DEFAULT));
+  auto wait_op = [](CUdeviceptr a, uint32_t v) {
+    CUstreamBatchMemOpParams o; memset(&o, 0, sizeof(o));
+    o.waitValue.operation = CU_STREAM_MEM_OP_WAIT_VALUE_32; o.waitValue.address = a; o.waitValue.value = v;
+    o.waitValue.flags = CU_STREAM_WAIT_VALUE_EQ;
+    return o;
+  };
+  auto write_op = [](CUdeviceptr a, uint32_t v) {
+    CUstreamBatchMemOpParams o; memset(&o, 0, sizeof(o));
+    o.writeValue.operation = CU_STREAM_MEM_OP_WRITE_VALUE_32; o.writeValue.address = a; o.writeValue.value = v;
+    o.writeValue.flags = CU_STREAM_WRITE_VALUE_DEFAULT;
+    return o;
+  };
+  auto submit = [&](cudaStream_t st, std::vector<CUstreamBatchMemOpParams>& ops) -> int {
+    CUstream cst = reinterpret_cast<CUstream>(st);
+    if (ops.empty()) return LOOPSB_OK;
+    if (P.batch) { CU_TRY(P.batch(cst, unsigned(ops.size()), ops.data(), 0)); }
+    else for (auto& o : ops) {
+      if (o.operation == CU_STREAM_MEM_OP_WAIT_VALUE_32) CU_TRY(P.wait32(cst, o.waitValue.address, o.waitValue.value, o.waitValue.flags));
+      else CU_TRY(P.write32(cst, o.writeValue.address, o.writeValue.value, o.writeValue.flags));
+    }
+    ops.clear();
+    return LOOPSB_OK;
+  };
+  // `start`: x_shard is ready and the previous step's kernels are done with x_full
   LOOPSB_CUDA_TRY(cudaEventRecord(d->start, s));
+  LOOPSB_CUDA_TRY(cudaMemcpyAsync(d->x_full + size_t(me) * d->chunk_cols, x_shard, chunk_b, cudaMemcpyDeviceToDevice, s));
+
+  // ---- publish: every peer is done with my stage[q] -> stage the shard -> raise the peers' flags
+  std::vector<CUstreamBatchMemOpParams> ops;
+  LOOPSB_CUDA_TRY(cudaStreamWaitEvent(P.pub, d->start, 0));
+  for (int p = 0; p < W; ++p) if (p != me) ops.push_back(wait_op(pulled_at(P.region, p), 1u));
+  for (int p = 0; p < W; ++p) if (p != me) ops.push_back(write_op(pulled_at(P.region, p), 0u));
+  if (int rc = submit(P.pub, ops)) return rc;
+  LOOPSB_CUDA_TRY(cudaMemcpyAsync(P.region + size_t(q) * P.stage_bytes, x_shard, chunk_b, cudaMemcpyDeviceToDevice, P.pub));
+  for (int sh = 1; sh < W; ++sh)             // the peer that pulls me first is told first
+    ops.push_back(write_op(ready_at(P.peer[size_t((me - sh + W) % W)], me), 1u));
+  if (int rc = submit(P.pub, ops)) return rc;
+  LOOPSB_CUDA_TRY(cudaEventRecord(P.published, P.pub));
+
+  // ---- pulls, ring order, spread over the copy streams
   for (cudaStream_t st : P.side) LOOPSB_CUDA_TRY(cudaStreamWaitEvent(st, d->start, 0));
   if (d->probing) LOOPSB_CUDA_TRY(cudaEventRecord(d->comm_begin, P.side[0]));
   int turn = 0;
@@ -340,21 +403,78 @@ int exchange_p2p(loopsb_dist* d, const float* x_shard, cudaStream_t s) {
     col_block& b = d->blocks[g];
     for (int sh : b.shifts) {
       const int p = (me + sh) % W;
-      cudaStream_t st = P.side[turn++ & 1];
-      CUstream cst = reinterpret_cast<CUstream>(st);
-      CU_TRY(P.wait32(cst, ready_at(P.region, p), k, CU_STREAM_WAIT_VALUE_GEQ));
+      cudaStream_t st = P.side[turn++ % K];
+      ops.push_back(wait_op(ready_at(P.region, p), 1u));
+      ops.push_back(write_op(ready_at(P.region, p), 0u));
+      if (int rc = submit(st, ops)) return rc;
       LOOPSB_CUDA_TRY(cudaMemcpyAsync(d->x_full + size_t(p) * d->chunk_cols, P.peer[size_t(p)] + size_t(q) * P.stage_bytes,
                                       chunk_b, cudaMemcpyDefault, st));
-      CU_TRY(P.write32(cst, pulled_at(P.peer[size_t(p)], me), k, CU_STREAM_WRITE_VALUE_DEFAULT));
+      ops.push_back(write_op(pulled_at(P.peer[size_t(p)], me), 1u));
+      if (int rc = submit(st, ops)) return rc;
     }
     LOOPSB_CUDA_TRY(cudaEventRecord(b.landed, P.side[0]));
-    LOOPSB_CUDA_TRY(cudaEventRecord(d->landed2[g], P.side[1]));
+    for (int j = 1; j < K; ++j) LOOPSB_CUDA_TRY(cudaEventRecord(d->landed_more[g * (K - 1) + (j - 1)], P.side[j]));
   }
   if (d->probing) {
-    LOOPSB_CUDA_TRY(cudaEventRecord(P.joined, P.side[1]));
-    LOOPSB_CUDA_TRY(cudaStreamWaitEvent(P.side[0], P.joined, 0));
+    for (int j = 1; j < K; ++j) {
+      LOOPSB_CUDA_TRY(cudaEventRecord(P.joined[j], P.side[j]));
+      LOOPSB_CUDA_TRY(cudaStreamWaitEvent(P.side[0], P.joined[j], 0));
+    }
     LOOPSB_CUDA_TRY(cudaEventRecord(d->comm_end, P.side[0]));
   }
+  return LOOPSB_OK;
+}
+
+// Everything one step enqueues when the shard is held as column blocks (also what is captured).
+int enqueue_split_step(loopsb_dist* d, const float* x_shard, float* y_shard, cudaStream_t s, uint32_t q) {
+  const nccl_api* n = nccl();
+  const size_t chunk = size_t(d->chunk_cols);
+  const bool probe = d->probing;
+  if (d->p2p.on) {
+    const int rc = exchange_p2p(d, x_shard, s, q);
+    if (rc != LOOPSB_OK) return rc;
+  } else {
+    // own chunk in place, then the ring-shifted NCCL phases on the side stream
+    if (chunk)
+      LOOPSB_CUDA_TRY(cudaMemcpyAsync(d->x_full + size_t(d->rank) * chunk, x_shard, chunk * sizeof(float),
+                                      cudaMemcpyDeviceToDevice, s));
+    LOOPSB_CUDA_TRY(cudaEventRecord(d->start, s));
+    LOOPSB_CUDA_TRY(cudaStreamWaitEvent(d->side, d->start, 0));
+    if (probe) LOOPSB_CUDA_TRY(cudaEventRecord(d->comm_begin, d->side));
+    for (size_t g = 1; g < d->blocks.size(); ++g) {
+      col_block& b = d->blocks[g];
+      NCCL_TRY(n->GroupStart());
+      for (int k : b.shifts) {
+        const int to = (d->rank - k + d->world) % d->world, from = (d->rank + k) % d->world;
+        NCCL_TRY(n->Send(x_shard, chunk, kNcclFloat32, to, d->comm, d->side));
+        NCCL_TRY(n->Recv(d->x_full + size_t(from) * chunk, chunk, kNcclFloat32, from, d->comm, d->side));
+      }
+      NCCL_TRY(n->GroupEnd());
+      LOOPSB_CUDA_TRY(cudaEventRecord(b.landed, d->side));
+    }
+    if (probe) LOOPSB_CUDA_TRY(cudaEventRecord(d->comm_end, d->side));
+  }
+  for (size_t g = 0; g < d->blocks.size(); ++g) {
+    col_block& b = d->blocks[g];
+    if (g > 0) LOOPSB_CUDA_TRY(cudaStreamWaitEvent(s, b.landed, 0));
+    if (g > 0 && d->p2p.on)
+      for (int j = 0; j < d->p2p.kPull - 1; ++j)
+        LOOPSB_CUDA_TRY(cudaStreamWaitEvent(s, d->landed_more[g * (d->p2p.kPull - 1) + j], 0));
+    if (probe) LOOPSB_CUDA_TRY(cudaEventRecord(b.k_begin, s));
+    const int rc = loopsb_spmv_f32(b.plan, b.values, b.indices, nullptr, d->x_full, g == 0 ? y_shard : b.y_part,
+                                   d->rows, d->cols, s);
+    if (rc != LOOPSB_OK) return rc;
+    if (g + 1 == d->blocks.size() && d->rows > 0) {
+      part_ptrs parts{};
+      for (size_t qq = 1; qq < d->blocks.size(); ++qq) parts.p[qq - 1] = d->blocks[qq].y_part;
+      const int grid = std::min((d->rows + 255) / 256, 148 * 8);
+      combine_parts_kernel<<<grid, 256, 0, s>>>(y_shard, parts, int(d->blocks.size()) - 1, d->rows);
+      LOOPSB_CUDA_TRY(cudaGetLastError());
+    }
+    if (probe) LOOPSB_CUDA_TRY(cudaEventRecord(b.k_end, s));
+  }
+  // x_shard is read by the publish stream too: in stream order it is free once this call's work is
+  if (d->p2p.on) LOOPSB_CUDA_TRY(cudaStreamWaitEvent(s, d->p2p.published, 0));
   return LOOPSB_OK;
 }
 }  // namespace
@@ -530,6 +650,7 @@ int loopsb_dist_info(const loopsb_dist_t* d, loopsb_dist_info_t* info) {
   if (d->world > 1 && nccl() && nccl()->GetVersion) nccl()->GetVersion(&v);
   info->nccl_version = v;
   info->transport = d->blocks.size() == 1 ? 0 : (d->p2p.on ? 2 : 1);
+  info->graphs_cached = int32_t(d->graphs.size());
   return LOOPSB_OK;
 }
 
@@ -588,47 +709,45 @@ int loopsb_dist_spmv(loopsb_dist_t* d, const float* x_shard, float* y_shard, voi
   }
 
   if (d->p2p.on) {
-    const int rc = exchange_p2p(d, x_shard, s);
-    if (rc != LOOPSB_OK) return rc;
-  } else {
-  // own chunk in place, then the ring-shifted phases on the side stream
-  if (chunk)
-    LOOPSB_CUDA_TRY(cudaMemcpyAsync(d->x_full + size_t(d->rank) * chunk, x_shard, chunk * sizeof(float),
-                                    cudaMemcpyDeviceToDevice, s));
-  LOOPSB_CUDA_TRY(cudaEventRecord(d->start, s));
-  LOOPSB_CUDA_TRY(cudaStreamWaitEvent(d->side, d->start, 0));
-  if (probe) LOOPSB_CUDA_TRY(cudaEventRecord(d->comm_begin, d->side));
-  for (size_t g = 1; g < d->blocks.size(); ++g) {
-    col_block& b = d->blocks[g];
-    NCCL_TRY(n->GroupStart());
-    for (int k : b.shifts) {
-      const int to = (d->rank - k + d->world) % d->world, from = (d->rank + k) % d->world;
-      NCCL_TRY(n->Send(x_shard, chunk, kNcclFloat32, to, d->comm, d->side));
-      NCCL_TRY(n->Recv(d->x_full + size_t(from) * chunk, chunk, kNcclFloat32, from, d->comm, d->side));
+    const uint32_t q = (++d->p2p.step) & 1u;
+    // replaying the step as one CUDA graph is opt-in: measured on 8 B200s it did not beat the
+    // ~70 individual calls (0.52 vs 0.50 ms per step), the step is bound by the chunks' arrival
+    static const bool no_graphs = getenv("LOOPSB_DIST_GRAPH") == nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &cap);
+    if (!d->use_graphs || no_graphs || probe || s == nullptr || cap != cudaStreamCaptureStatusNone)
+      return enqueue_split_step(d, x_shard, y_shard, s, q);
+    for (auto& g : d->graphs)
+      if (g.x == x_shard && g.y == y_shard && g.q == q) {
+        LOOPSB_CUDA_TRY(cudaGraphLaunch(g.exec, s));
+        return LOOPSB_OK;
+      }
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+      (void)cudaGetLastError();
+      d->use_graphs = false;
+      return enqueue_split_step(d, x_shard, y_shard, s, q);
     }
-    NCCL_TRY(n->GroupEnd());
-    LOOPSB_CUDA_TRY(cudaEventRecord(b.landed, d->side));
-  }
-  if (probe) LOOPSB_CUDA_TRY(cudaEventRecord(d->comm_end, d->side));
-  }
-  for (size_t g = 0; g < d->blocks.size(); ++g) {
-    col_block& b = d->blocks[g];
-    if (g > 0) LOOPSB_CUDA_TRY(cudaStreamWaitEvent(s, b.landed, 0));
-    if (g > 0 && d->p2p.on) LOOPSB_CUDA_TRY(cudaStreamWaitEvent(s, d->landed2[g], 0));
-    if (probe) LOOPSB_CUDA_TRY(cudaEventRecord(b.k_begin, s));
-    const int rc = loopsb_spmv_f32(b.plan, b.values, b.indices, nullptr, d->x_full, g == 0 ? y_shard : b.y_part,
-                                   d->rows, d->cols, s);
-    if (rc != LOOPSB_OK) return rc;
-    if (g + 1 == d->blocks.size() && d->rows > 0) {
-      part_ptrs parts{};
-      for (size_t q = 1; q < d->blocks.size(); ++q) parts.p[q - 1] = d->blocks[q].y_part;
-      const int grid = std::min((d->rows + 255) / 256, 148 * 8);
-      combine_parts_kernel<<<grid, 256, 0, s>>>(y_shard, parts, int(d->blocks.size()) - 1, d->rows);
-      LOOPSB_CUDA_TRY(cudaGetLastError());
+    const int rc = enqueue_split_step(d, x_shard, y_shard, s, q);
+    const cudaError_t ee = cudaStreamEndCapture(s, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (rc != LOOPSB_OK || ee != cudaSuccess || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+      // capture refused (old driver, unsupported node): run this and every later step directly
+      (void)cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      d->use_graphs = false;
+      return enqueue_split_step(d, x_shard, y_shard, s, q);
     }
-    if (probe) LOOPSB_CUDA_TRY(cudaEventRecord(b.k_end, s));
+    cudaGraphDestroy(graph);
+    if (d->graphs.size() >= 16) {              // callers cycling through many buffers: drop the oldest
+      cudaGraphExecDestroy(d->graphs.front().exec);
+      d->graphs.erase(d->graphs.begin());
+    }
+    d->graphs.push_back({x_shard, y_shard, q, exec});
+    LOOPSB_CUDA_TRY(cudaGraphLaunch(exec, s));
+    return LOOPSB_OK;
   }
-  return LOOPSB_OK;
+  return enqueue_split_step(d, x_shard, y_shard, s, 0);
 }
 
 }  // extern "C"

@@ -119,7 +119,7 @@ def default_groups(world: int):
     if env is not None:
         env = env.strip()
         return [] if env in ("", "0", "none") else [int(t) for t in env.split(",")]
-    return {1: [], 2: [1], 4: [1, 2], 8: [3, 4]}.get(world, [world - 1] if world > 1 else [])
+    return {1: [], 2: [1], 4: [1, 2], 8: []}.get(world, [])
 
 
 class DistPlan:
@@ -174,7 +174,7 @@ class DistPlan:
         i = _lib.DistInfo()
         _lib.check(self._lib.loopsb_dist_info(self.handle, C.byref(i)), "loopsb_dist_info")
         d = {n: int(getattr(i, n)) for n in ("world", "rank", "local_rows", "num_cols", "num_blocks",
-                                             "nccl_version", "local_nnz", "bytes")}
+                                             "nccl_version", "local_nnz", "bytes", "graphs_cached")}
         d["transport"] = {0: "one ncclAllGather", 1: "nccl send/recv phases",
                           2: "copy-engine pulls over CUDA IPC (stream memory ops)"}[int(i.transport)]
         d["block_nnz"] = [int(v) for v in i.block_nnz][: d["num_blocks"]]
