@@ -241,6 +241,85 @@ inline void group_mapped(csr_t<int, int, double>& csr, vector_t<double>& x, vect
   detail::run_f64(csr, LOOPSB_SCHED_GROUP_MAPPED, x, y, stream);
 }
 
+// ---- fp64 for the other in-tree formats (every reference example is also built as .f64) ----
+namespace detail {
+inline util::timer_t run_layout_f64(const loopsb_layout_t& lay, int schedule, const double* values, const int* cols,
+                                    const int* rows_idx, const double* x, double* y, std::size_t nrows,
+                                    std::size_t ncols, cudaStream_t stream) {
+  util::timer_t timer(stream);
+  timer.start();
+  error::throw_if_status(loopsb_spmv_layout_f64(&lay, schedule, values, cols, rows_idx, x, y, static_cast<int32_t>(nrows),
+                                                static_cast<int32_t>(ncols), stream),
+                         "loopsb_spmv_layout_f64");
+  cudaStreamSynchronize(stream);
+  timer.stop();
+  return timer;
+}
+}  // namespace detail
+
+inline void original(csr_t<int, int, double>& csr, vector_t<double>& x, vector_t<double>& y, cudaStream_t stream = 0) {
+  thread_mapped(csr, x, y, stream);
+}
+inline util::timer_t coo_thread_mapped(coo_t<int, double>& coo, vector_t<double>& x, vector_t<double>& y,
+                                       cudaStream_t stream = 0) {
+  layout::coo<int, int> lay(static_cast<int>(coo.nnzs));
+  return detail::run_layout_f64(lay.descriptor(), LOOPSB_SCHED_THREAD_MAPPED, detail::raw(coo.values),
+                                detail::raw(coo.col_indices), detail::raw(coo.row_indices), detail::raw(x),
+                                detail::raw(y), coo.rows, coo.cols, stream);
+}
+inline void ell_thread_mapped(ell_t<int, double>& ell, vector_t<double>& x, vector_t<double>& y,
+                              cudaStream_t stream = 0) {
+  detail::run_layout_f64(ell.layout().descriptor(), LOOPSB_SCHED_THREAD_MAPPED, detail::raw(ell.values),
+                         detail::raw(ell.indices), nullptr, detail::raw(x), detail::raw(y), ell.rows, ell.cols, stream);
+}
+inline util::timer_t ell_merge_path(ell_t<int, double>& ell, vector_t<double>& x, vector_t<double>& y,
+                                    cudaStream_t stream = 0) {
+  return detail::run_layout_f64(ell.layout().descriptor(), LOOPSB_SCHED_MERGE_PATH_FLAT, detail::raw(ell.values),
+                                detail::raw(ell.indices), nullptr, detail::raw(x), detail::raw(y), ell.rows, ell.cols,
+                                stream);
+}
+inline util::timer_t csc_thread_mapped(csc_t<int, int, double>& csc, vector_t<double>& x, vector_t<double>& y,
+                                       cudaStream_t stream = 0) {
+  return detail::run_layout_f64(csc.layout().descriptor(), LOOPSB_SCHED_THREAD_MAPPED, detail::raw(csc.values),
+                                detail::raw(csc.indices), nullptr, detail::raw(x), detail::raw(y), csc.rows, csc.cols,
+                                stream);
+}
+template <std::size_t K = 8>
+util::timer_t flat_partitioned(csr_t<int, int, double>& csr, vector_t<double>& x, vector_t<double>& y,
+                               cudaStream_t stream = 0) {
+  layout::flat_uniform_occupancy<K, layout::csr<int, int>> lay(csr.layout());
+  return detail::run_layout_f64(lay.descriptor(), LOOPSB_SCHED_THREAD_MAPPED, detail::raw(csr.values),
+                                detail::raw(csr.indices), nullptr, detail::raw(x), detail::raw(y), csr.rows, csr.cols,
+                                stream);
+}
+inline util::timer_t dia_thread_mapped(dia_t<int, int, double>& dia, vector_t<double>& x, vector_t<double>& y,
+                                       cudaStream_t stream = 0) {
+  util::timer_t timer(stream);
+  timer.start();
+  error::throw_if_status(
+      loopsb_spmv_dia_f64(static_cast<int32_t>(dia.rows), static_cast<int32_t>(dia.cols),
+                          static_cast<int64_t>(dia.stride), static_cast<int32_t>(dia.num_diagonals),
+                          detail::raw(dia.diag_offsets), detail::raw(dia.values), detail::raw(x), detail::raw(y), stream),
+      "loopsb_spmv_dia_f64");
+  cudaStreamSynchronize(stream);
+  timer.stop();
+  return timer;
+}
+template <std::size_t R, std::size_t C>
+util::timer_t bcsr_thread_mapped(bcsr_t<R, C, int, int, double>& bcsr, vector_t<double>& x, vector_t<double>& y,
+                                 cudaStream_t stream = 0) {
+  const loopsb_layout_t lay = bcsr.layout().descriptor();
+  util::timer_t timer(stream);
+  timer.start();
+  error::throw_if_status(loopsb_spmv_bcsr_f64(int32_t(R), int32_t(C), &lay, detail::raw(bcsr.values),
+                                              detail::raw(bcsr.block_col_indices), detail::raw(x), detail::raw(y),
+                                              static_cast<int32_t>(bcsr.rows), stream),
+                         "loopsb_spmv_bcsr_f64");
+  cudaStreamSynchronize(stream);
+  timer.stop();
+  return timer;
+}
+
 /// The schedule the library would pick for this matrix (the
 /// reference publishes its heuristic's outcomes in plots/data/heuristics.csv).
 /// The widest row is computed on the device.

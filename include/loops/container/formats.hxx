@@ -65,13 +65,39 @@ struct coo_t {
   coo_t(const csr_t<index_t, offset_t, value_t, rhs_space>& csr);
 
   /// Row-major (row, col) ordering; ties keep their input order.
-  void sort_by_row() {
+  void sort_by_row() { reorder(true); }
+
+  /// Column-major (col, row) ordering (reference container/coo.hxx:116-122); the values
+  /// travel with their coordinates.
+  void sort_by_column() { reorder(false); }
+
+  /// Sort by (row, col) and keep the first entry of every coordinate pair
+  /// (reference container/coo.hxx:128-145).
+  void remove_duplicates() {
+    sort_by_row();
+    thrust::host_vector<index_t> r(row_indices), c(col_indices);
+    thrust::host_vector<value_t> v(values);
+    std::size_t kept = 0;
+    for (std::size_t i = 0; i < nnzs; ++i) {
+      if (kept > 0 && r[i] == r[kept - 1] && c[i] == c[kept - 1]) continue;
+      r[kept] = r[i]; c[kept] = c[i]; v[kept] = v[i];
+      ++kept;
+    }
+    r.resize(kept); c.resize(kept); v.resize(kept);
+    nnzs = kept;
+    row_indices = r; col_indices = c; values = v;
+  }
+
+ private:
+  void reorder(bool by_row) {
     thrust::host_vector<index_t> r(row_indices), c(col_indices);
     thrust::host_vector<value_t> v(values);
     std::vector<std::size_t> perm(nnzs);
     std::iota(perm.begin(), perm.end(), std::size_t(0));
     std::stable_sort(perm.begin(), perm.end(), [&](std::size_t a, std::size_t b) {
-      return r[a] != r[b] ? r[a] < r[b] : c[a] < c[b];
+      const index_t ka = by_row ? r[a] : c[a], kb = by_row ? r[b] : c[b];
+      const index_t ta = by_row ? c[a] : r[a], tb = by_row ? c[b] : r[b];
+      return ka != kb ? ka < kb : ta < tb;
     });
     thrust::host_vector<index_t> r2(nnzs), c2(nnzs);
     thrust::host_vector<value_t> v2(nnzs);
@@ -317,6 +343,20 @@ struct csc_t {
   csc_t(const csc_t<index_t, offset_t, value_t, rhs_space>& rhs)
       : rows(rhs.rows), cols(rhs.cols), nnzs(rhs.nnzs),
         offsets(rhs.offsets), indices(rhs.indices), values(rhs.values) {}
+
+  /// From COO (reference container/csc.hxx:85-93): entries ordered by (column, row),
+  /// column offsets by counting.
+  template <auto rhs_space>
+  csc_t(const coo_t<index_t, value_t, rhs_space>& coo) : rows(coo.rows), cols(coo.cols), nnzs(coo.nnzs) {
+    coo_t<index_t, value_t, memory_space_t::host> sorted(coo);
+    sorted.sort_by_column();
+    thrust::host_vector<offset_t> c_off(cols + 1, offset_t(0));
+    for (std::size_t a = 0; a < nnzs; ++a) c_off[sorted.col_indices[a] + 1] += 1;
+    for (std::size_t c = 0; c < cols; ++c) c_off[c + 1] += c_off[c];
+    offsets = c_off;
+    indices = sorted.row_indices;
+    values = sorted.values;
+  }
 
   /// From CSR: stable counting sort by column over CSR order.
   template <auto rhs_space>

@@ -12,6 +12,9 @@
  * a plain value type and nothing depends on <iterator>.
  */
 #pragma once
+#include <initializer_list>
+#include <type_traits>
+#include <utility>
 
 #include <cstddef>
 
@@ -110,6 +113,29 @@ using step_range_t = step_range<T>;
 template <typename T, std::size_t N>
 LOOPS_HD step_range<std::size_t> indices(T (&)[N]) {
   return step_range<std::size_t>(0, N, 1);
+}
+
+namespace traits {
+/// Does `C` have a `size()` returning an integer?
+template <typename C, typename = void>
+struct has_size : std::false_type {};
+template <typename C>
+struct has_size<C, std::enable_if_t<std::is_integral<decltype(std::declval<const C&>().size())>::value>>
+    : std::true_type {};
+}  // namespace traits
+
+/// `for (auto i : indices(container))` -- host only (a container's size() is a host function).
+template <typename C, typename = std::enable_if_t<traits::has_size<C>::value>>
+__host__ auto indices(const C& cont) -> step_range<decltype(cont.size())> {
+  using size_type = decltype(cont.size());
+  return step_range<size_type>(size_type(0), cont.size(), size_type(1));
+}
+
+/// `for (auto i : indices({a, b, c}))`.
+template <typename T>
+LOOPS_HD step_range<typename std::initializer_list<T>::size_type> indices(std::initializer_list<T>&& cont) {
+  using size_type = typename std::initializer_list<T>::size_type;
+  return step_range<size_type>(size_type(0), cont.size(), size_type(1));
 }
 
 }  // namespace loops

@@ -466,6 +466,22 @@ int loopsb_spmv_f64(const loopsb_layout_t* lay, int schedule, const double* valu
                     const int32_t* col_indices, const double* x, double* y,
                     int32_t num_rows, int32_t num_cols, void* stream);
 
+/* The other in-tree layouts in double -- COO / CSC / flat_uniform_occupancy (thread_mapped),
+ * ELL (thread_mapped, merge_path_flat), CSR (forwards to loopsb_spmv_f64); same argument meaning
+ * as loopsb_spmv_f32 -- and DIA / BCSR like their fp32 entry points. The reference's entry points
+ * are templates on type_t and every example is also built as .f64
+ * (examples/spmv/CMakeLists.txt:29). Same thread->work maps as the fp32 kernels, un-fused
+ * arithmetic, y fully overwritten; not tuned (fp64 is not a BASELINE config). */
+int loopsb_spmv_layout_f64(const loopsb_layout_t* lay, int schedule, const double* values,
+                           const int32_t* col_indices, const int32_t* row_indices, const double* x,
+                           double* y, int32_t num_rows, int32_t num_cols, void* stream);
+int loopsb_spmv_dia_f64(int32_t num_rows, int32_t num_cols, int64_t stride, int32_t num_diagonals,
+                        const int32_t* diag_offsets, const double* values, const double* x, double* y,
+                        void* stream);
+int loopsb_spmv_bcsr_f64(int32_t R, int32_t C, const loopsb_layout_t* lay, const double* values,
+                         const int32_t* block_col_indices, const double* x_padded, double* y,
+                         int32_t num_rows, void* stream);
+
 /* Which schedule to run for a CSR matrix (the
  * reference publishes the outcome of its heuristic per matrix in
  * plots/data/heuristics.csv). max_degree < 0 = unknown (then only nnz decides,

@@ -116,6 +116,9 @@ SIGNATURES = {
                                        _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _P]),
     "loopsb_work_oriented_grid": (C.c_int, [C.POINTER(C.c_int32)]),
     "loopsb_spmv_f64": (C.c_int, [C.POINTER(LayoutDesc), C.c_int, _P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "loopsb_spmv_layout_f64": (C.c_int, [C.POINTER(LayoutDesc), C.c_int, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "loopsb_spmv_dia_f64": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _P, _P]),
+    "loopsb_spmv_bcsr_f64": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(LayoutDesc), _P, _P, _P, _P, C.c_int32, _P]),
     "loopsb_select_schedule": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.POINTER(C.c_int32)]),
     # format conversions on the device
     "loopsb_csr_to_coo": (C.c_int, [C.c_int32, C.c_int64, _P, _P, _P]),

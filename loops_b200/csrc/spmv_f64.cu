@@ -78,7 +78,203 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// ---- the other in-tree layouts in double (the reference builds every example as .f64 too,
+// examples/spmv/CMakeLists.txt:29). Same thread->work maps as the fp32 kernels of
+// spmv_schedules.cuh, un-fused multiply / add; the scatter formats accumulate with fp64 atomics
+// into a y the library zeroes, exactly where the reference's kernels use atomics.
+__global__ void __launch_bounds__(kThreads)
+    coo_f64_kernel(const int* __restrict__ row, const int* __restrict__ col, const double* __restrict__ val,
+                   const double* __restrict__ x, double* __restrict__ y, long long nnz) {
+  const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < nnz) atomicAdd(&y[row[a]], __dmul_rn(val[a], x[col[a]]));
+}
+
+__global__ void __launch_bounds__(kThreads)
+    ell_f64_thread_kernel(const int* __restrict__ idx, const double* __restrict__ val, const double* __restrict__ x,
+                          double* __restrict__ y, int rows, int pitch) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const long long first = (long long)r * pitch;
+  double sum = 0.0;
+  for (int s = 0; s < pitch; ++s) {
+    const int c = idx[first + s];
+    if (c >= 0) sum = __dadd_rn(sum, __dmul_rn(val[first + s], x[c]));
+  }
+  y[r] = sum;
+}
+
+// ell_merge_path in double: a warp per row, lanes stride over the row's slots (coalesced), shuffle tree.
+__global__ void __launch_bounds__(kThreads)
+    ell_f64_warp_kernel(const int* __restrict__ idx, const double* __restrict__ val, const double* __restrict__ x,
+                        double* __restrict__ y, int rows, int pitch) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const long long first = (long long)r * pitch;
+  double sum = 0.0;
+  for (int s = lane; s < pitch; s += 32) {
+    const int c = idx[first + s];
+    if (c >= 0) sum = __dadd_rn(sum, __dmul_rn(val[first + s], x[c]));
+  }
+  for (int d = 16; d > 0; d >>= 1) sum = __dadd_rn(sum, __shfl_down_sync(0xffffffffu, sum, d));
+  if (lane == 0) y[r] = sum;
+}
+
+__global__ void __launch_bounds__(kThreads)
+    csc_f64_kernel(const int* __restrict__ off, const int* __restrict__ row, const double* __restrict__ val,
+                   const double* __restrict__ x, double* __restrict__ y, int cols) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const double xc = x[c];
+  for (int a = off[c]; a < off[c + 1]; ++a) atomicAdd(&y[row[a]], __dmul_rn(val[a], xc));
+}
+
+__global__ void __launch_bounds__(kThreads)
+    flat_f64_kernel(const int* __restrict__ off, const int* __restrict__ idx, const double* __restrict__ val,
+                    const double* __restrict__ x, double* __restrict__ y, int rows, int nnz, int K) {
+  const long long windows = ((long long)nnz + K - 1) / K;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= windows) return;
+  const int a0 = int(t * K), a1 = min(nnz, a0 + K);
+  int lo = 0, hi = rows;                       // offsets[lo] <= a0 < offsets[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= a0) lo = mid; else hi = mid;
+  }
+  int r = lo, r_end = off[r + 1];
+  double acc = 0.0;
+  for (int a = a0; a < a1; ++a) {
+    while (a >= r_end) {
+      if (acc != 0.0) atomicAdd(&y[r], acc);
+      acc = 0.0;
+      ++r;
+      r_end = off[r + 1];
+    }
+    acc = __dadd_rn(acc, __dmul_rn(val[a], x[idx[a]]));
+  }
+  if (acc != 0.0) atomicAdd(&y[r], acc);
+}
+
+__global__ void __launch_bounds__(kThreads)
+    dia_f64_kernel(const int* __restrict__ diag, const double* __restrict__ val, const double* __restrict__ x,
+                   double* __restrict__ y, int rows, int cols, long long stride, int nd) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  double acc = 0.0;
+  for (int d = 0; d < nd; ++d) {
+    const long long c = (long long)r + diag[d];
+    if (c >= 0 && c < cols) acc = __dadd_rn(acc, __dmul_rn(val[(long long)d * stride + r], x[c]));
+  }
+  y[r] = acc;
+}
+
+template <int R, int C>
+__global__ void __launch_bounds__(kThreads)
+    bcsr_f64_kernel(const int* __restrict__ boff, const int* __restrict__ bcol, const double* __restrict__ val,
+                    const double* __restrict__ x, double* __restrict__ y, int block_rows, int rows) {
+  const int br = blockIdx.x * blockDim.x + threadIdx.x;
+  if (br >= block_rows) return;
+  double acc[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) acc[i] = 0.0;
+  for (int b = boff[br]; b < boff[br + 1]; ++b) {
+    const long long bc = bcol[b];
+    const double* blk = val + (long long)b * R * C;
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+      for (int j = 0; j < C; ++j) acc[i] = __dadd_rn(acc[i], __dmul_rn(blk[i * C + j], x[bc * C + j]));
+  }
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+    if ((long long)br * R + i < rows) y[(long long)br * R + i] = acc[i];
+}
+
 }  // namespace
+
+extern "C" int loopsb_spmv_layout_f64(const loopsb_layout_t* lay, int schedule, const double* values,
+                                      const int32_t* col_indices, const int32_t* row_indices, const double* x,
+                                      double* y, int32_t num_rows, int32_t num_cols, void* stream) {
+  LOOPSB_REQUIRE(lay != nullptr, "layout is null");
+  if (lay->kind == LOOPSB_LAYOUT_CSR)
+    return loopsb_spmv_f64(lay, schedule, values, col_indices, x, y, num_rows, num_cols, stream);
+  LOOPSB_REQUIRE(num_rows >= 0 && num_cols >= 0 && lay->num_atoms >= 0 && lay->num_tiles >= 0, "bad dimensions");
+  if (current_device() == nullptr) return LOOPSB_ERR_CUDA;
+  if (num_rows == 0) return LOOPSB_OK;
+  LOOPSB_REQUIRE(y != nullptr, "y is null");
+  cudaStream_t s = as_stream(stream);
+  const long long A = lay->num_atoms;
+  if (A == 0) {
+    LOOPSB_CUDA_TRY(cudaMemsetAsync(y, 0, size_t(num_rows) * sizeof(double), s));
+    return LOOPSB_OK;
+  }
+  LOOPSB_REQUIRE(values && col_indices && x, "null matrix / x pointer");
+  auto blocks = [](long long n) { return unsigned((n + kThreads - 1) / kThreads); };
+  switch (lay->kind) {
+    case LOOPSB_LAYOUT_COO:
+      LOOPSB_REQUIRE(schedule == LOOPSB_SCHED_THREAD_MAPPED && row_indices != nullptr, "COO: thread_mapped with row ids");
+      LOOPSB_CUDA_TRY(cudaMemsetAsync(y, 0, size_t(num_rows) * sizeof(double), s));
+      coo_f64_kernel<<<blocks(A), kThreads, 0, s>>>(row_indices, col_indices, values, x, y, A);
+      break;
+    case LOOPSB_LAYOUT_ELL:
+      LOOPSB_REQUIRE(lay->num_tiles == num_rows && lay->pitch >= 0, "ELL: tiles must equal rows");
+      if (schedule == LOOPSB_SCHED_THREAD_MAPPED)
+        ell_f64_thread_kernel<<<blocks(num_rows), kThreads, 0, s>>>(col_indices, values, x, y, num_rows, lay->pitch);
+      else if (schedule == LOOPSB_SCHED_MERGE_PATH_FLAT)
+        ell_f64_warp_kernel<<<blocks((long long)num_rows * 32), kThreads, 0, s>>>(col_indices, values, x, y, num_rows,
+                                                                                   lay->pitch);
+      else { set_error("ELL in double: thread_mapped or merge_path_flat"); return LOOPSB_ERR_UNSUPPORTED; }
+      break;
+    case LOOPSB_LAYOUT_CSC:
+      LOOPSB_REQUIRE(schedule == LOOPSB_SCHED_THREAD_MAPPED && lay->offsets && lay->num_tiles == num_cols, "CSC: thread_mapped over columns");
+      LOOPSB_CUDA_TRY(cudaMemsetAsync(y, 0, size_t(num_rows) * sizeof(double), s));
+      csc_f64_kernel<<<blocks(num_cols), kThreads, 0, s>>>(lay->offsets, col_indices, values, x, y, num_cols);
+      break;
+    case LOOPSB_LAYOUT_FLAT:
+      LOOPSB_REQUIRE(schedule == LOOPSB_SCHED_THREAD_MAPPED && lay->offsets && lay->pitch > 0, "flat_uniform_occupancy: thread_mapped, K > 0");
+      LOOPSB_CUDA_TRY(cudaMemsetAsync(y, 0, size_t(num_rows) * sizeof(double), s));
+      flat_f64_kernel<<<blocks((A + lay->pitch - 1) / lay->pitch), kThreads, 0, s>>>(lay->offsets, col_indices, values, x, y,
+                                                                                     num_rows, int(A), lay->pitch);
+      break;
+    default:
+      set_error("no fp64 SpMV for this layout kind here (DIA / BCSR have their own entry points)");
+      return LOOPSB_ERR_UNSUPPORTED;
+  }
+  LOOPSB_CUDA_TRY(cudaGetLastError());
+  return LOOPSB_OK;
+}
+
+extern "C" int loopsb_spmv_dia_f64(int32_t num_rows, int32_t num_cols, int64_t stride, int32_t num_diagonals,
+                                   const int32_t* diag_offsets, const double* values, const double* x, double* y,
+                                   void* stream) {
+  LOOPSB_REQUIRE(num_rows >= 0 && num_cols >= 0 && num_diagonals >= 0 && stride >= num_rows, "bad dimensions");
+  if (current_device() == nullptr) return LOOPSB_ERR_CUDA;
+  if (num_rows == 0) return LOOPSB_OK;
+  LOOPSB_REQUIRE(y != nullptr && (num_diagonals == 0 || (diag_offsets && values && x)), "null pointer");
+  dia_f64_kernel<<<(num_rows + kThreads - 1) / kThreads, kThreads, 0, as_stream(stream)>>>(
+      diag_offsets, values, x, y, num_rows, num_cols, stride, num_diagonals);
+  LOOPSB_CUDA_TRY(cudaGetLastError());
+  return LOOPSB_OK;
+}
+
+extern "C" int loopsb_spmv_bcsr_f64(int32_t R, int32_t C, const loopsb_layout_t* lay, const double* values,
+                                    const int32_t* block_col_indices, const double* x_padded, double* y,
+                                    int32_t num_rows, void* stream) {
+  LOOPSB_REQUIRE(lay != nullptr && lay->kind == LOOPSB_LAYOUT_BCSR && lay->offsets != nullptr, "BCSR layout required");
+  LOOPSB_REQUIRE(num_rows >= 0, "negative rows");
+  if (current_device() == nullptr) return LOOPSB_ERR_CUDA;
+  if (num_rows == 0 || lay->num_tiles == 0) return LOOPSB_OK;
+  LOOPSB_REQUIRE(y != nullptr && (lay->num_atoms == 0 || (values && block_col_indices && x_padded)), "null pointer");
+  const int br = lay->num_tiles;
+  const unsigned grid = unsigned((br + kThreads - 1) / kThreads);
+  cudaStream_t s = as_stream(stream);
+  if (R == 2 && C == 2) bcsr_f64_kernel<2, 2><<<grid, kThreads, 0, s>>>(lay->offsets, block_col_indices, values, x_padded, y, br, num_rows);
+  else if (R == 3 && C == 3) bcsr_f64_kernel<3, 3><<<grid, kThreads, 0, s>>>(lay->offsets, block_col_indices, values, x_padded, y, br, num_rows);
+  else if (R == 4 && C == 4) bcsr_f64_kernel<4, 4><<<grid, kThreads, 0, s>>>(lay->offsets, block_col_indices, values, x_padded, y, br, num_rows);
+  else { set_error("BCSR block shape %dx%d not instantiated (2x2, 3x3, 4x4)", R, C); return LOOPSB_ERR_UNSUPPORTED; }
+  LOOPSB_CUDA_TRY(cudaGetLastError());
+  return LOOPSB_OK;
+}
 
 extern "C" int loopsb_spmv_f64(const loopsb_layout_t* lay, int schedule, const double* values,
                                const int32_t* col_indices, const double* x, double* y, int32_t num_rows,
