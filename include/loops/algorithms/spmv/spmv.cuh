@@ -151,6 +151,39 @@ inline util::timer_t ell_merge_path(ell_t<int, float>& ell, vector_t<float>& x, 
                      stream);
 }
 
+// ---- the five (schedule x layout) cells of BASELINE configs[2] the reference has no kernel for:
+// schedule::setup<scheme, ..., layout> over the COO / ELL view with the format's per-atom body
+// (loops_b200/csrc/spmv_generic.cu). New entry points, same argument meaning. ----
+inline util::timer_t coo_group_mapped(coo_t<int, float>& coo, vector_t<float>& x, vector_t<float>& y,
+                                      cudaStream_t stream = 0) {
+  layout::coo<int, int> lay(static_cast<int>(coo.nnzs));
+  return detail::run(lay.descriptor(), LOOPSB_SCHED_GROUP_MAPPED, detail::raw(coo.values), detail::raw(coo.col_indices),
+                     detail::raw(coo.row_indices), detail::raw(x), detail::raw(y), coo.rows, coo.cols, stream);
+}
+inline util::timer_t coo_work_oriented(coo_t<int, float>& coo, vector_t<float>& x, vector_t<float>& y,
+                                       cudaStream_t stream = 0) {
+  layout::coo<int, int> lay(static_cast<int>(coo.nnzs));
+  return detail::run(lay.descriptor(), LOOPSB_SCHED_WORK_ORIENTED, detail::raw(coo.values), detail::raw(coo.col_indices),
+                     detail::raw(coo.row_indices), detail::raw(x), detail::raw(y), coo.rows, coo.cols, stream);
+}
+inline util::timer_t coo_merge_path(coo_t<int, float>& coo, vector_t<float>& x, vector_t<float>& y,
+                                    cudaStream_t stream = 0) {
+  layout::coo<int, int> lay(static_cast<int>(coo.nnzs));
+  return detail::run(lay.descriptor(), LOOPSB_SCHED_MERGE_PATH_FLAT, detail::raw(coo.values),
+                     detail::raw(coo.col_indices), detail::raw(coo.row_indices), detail::raw(x), detail::raw(y),
+                     coo.rows, coo.cols, stream);
+}
+inline util::timer_t ell_group_mapped(ell_t<int, float>& ell, vector_t<float>& x, vector_t<float>& y,
+                                      cudaStream_t stream = 0) {
+  return detail::run(ell.layout().descriptor(), LOOPSB_SCHED_GROUP_MAPPED, detail::raw(ell.values),
+                     detail::raw(ell.indices), nullptr, detail::raw(x), detail::raw(y), ell.rows, ell.cols, stream);
+}
+inline util::timer_t ell_work_oriented(ell_t<int, float>& ell, vector_t<float>& x, vector_t<float>& y,
+                                       cudaStream_t stream = 0) {
+  return detail::run(ell.layout().descriptor(), LOOPSB_SCHED_WORK_ORIENTED, detail::raw(ell.values),
+                     detail::raw(ell.indices), nullptr, detail::raw(x), detail::raw(y), ell.rows, ell.cols, stream);
+}
+
 /// reference algorithms/spmv/original.cuh:55-72 -- the plain one-thread-per-row kernel; same
 /// arithmetic as thread_mapped (sequential per row), so it is the same sm_100a kernel.
 inline void original(csr_t<int, int, float>& csr, vector_t<float>& x, vector_t<float>& y,

@@ -204,6 +204,44 @@ def bcsr_thread_mapped(bcsr: bcsr_t, x, y, stream=None, sync=True, repack=False)
     return timer
 
 
+# ---- the (schedule x layout) cells of BASELINE configs[2] without a kernel in the reference
+# tree: schedule::setup<scheme, ..., layout> + the format's per-atom body (SURVEY 8 a17;
+# loops_b200/csrc/spmv_generic.cu). Same argument meaning as the in-tree entry points.
+def coo_group_mapped(coo: coo_t, x, y, stream=None, sync=True):
+    return _run(coo, _lib.SCHED_GROUP_MAPPED, coo.values, coo.col_indices, coo.row_indices, x, y, coo.rows, coo.cols,
+                stream, sync, timed=True)
+
+
+def coo_work_oriented(coo: coo_t, x, y, stream=None, sync=True):
+    return _run(coo, _lib.SCHED_WORK_ORIENTED, coo.values, coo.col_indices, coo.row_indices, x, y, coo.rows, coo.cols,
+                stream, sync, timed=True)
+
+
+def coo_merge_path(coo: coo_t, x, y, stream=None, sync=True):
+    return _run(coo, _lib.SCHED_MERGE_PATH_FLAT, coo.values, coo.col_indices, coo.row_indices, x, y, coo.rows,
+                coo.cols, stream, sync, timed=True)
+
+
+def ell_group_mapped(ell: ell_t, x, y, stream=None, sync=True):
+    return _run(ell, _lib.SCHED_GROUP_MAPPED, ell.values, ell.indices, None, x, y, ell.rows, ell.cols, stream, sync,
+                timed=True)
+
+
+def ell_work_oriented(ell: ell_t, x, y, stream=None, sync=True):
+    return _run(ell, _lib.SCHED_WORK_ORIENTED, ell.values, ell.indices, None, x, y, ell.rows, ell.cols, stream, sync,
+                timed=True)
+
+
+# every cell of the {thread_mapped, group_mapped, work_oriented, merge_path_flat} x {csr, coo, ell} grid
+CELLS = {
+    ("csr", "thread_mapped"): thread_mapped, ("csr", "group_mapped"): group_mapped,
+    ("csr", "work_oriented"): work_oriented, ("csr", "merge_path_flat"): merge_path_flat,
+    ("coo", "thread_mapped"): coo_thread_mapped, ("coo", "group_mapped"): coo_group_mapped,
+    ("coo", "work_oriented"): coo_work_oriented, ("coo", "merge_path_flat"): coo_merge_path,
+    ("ell", "thread_mapped"): ell_thread_mapped, ("ell", "group_mapped"): ell_group_mapped,
+    ("ell", "work_oriented"): ell_work_oriented, ("ell", "merge_path_flat"): ell_merge_path,
+}
+
 BY_NAME = {
     "merge_path_flat": merge_path_flat,
     "work_oriented": work_oriented,

@@ -62,6 +62,16 @@ const device_props* current_device() {
 
 using namespace loopsb;
 
+// spmv_generic.cu: the (schedule x layout) cells without a reference kernel
+namespace loopsb { namespace generic {
+struct state;
+int create(state** out, const loopsb_layout_t* lay, int schedule, int wo_grid, cudaStream_t s);
+void destroy(state* st);
+bool supports(int kind, int schedule);
+int run(state* st, const loopsb_layout_t* lay, int schedule, const float* values, const int* cols, const int* rows,
+        const float* x, float* y, int num_rows, cudaStream_t s);
+}}  // namespace loopsb::generic
+
 // Merge-path SpMV geometry variants: {CTA threads, merge tiles per CTA tile,
 // stages, target CTAs/SM}. Variant 0 is the default; LOOPSB_MERGE_VARIANT
 // selects another one at plan creation (tuning aid).
@@ -231,6 +241,7 @@ struct loopsb_plan {
   int gen = 1;        // merge kernel generation (2 = spmv_merge2.cuh, needs 16-byte aligned arrays)
   int variant2 = -1;  // index into kMerge2Variants forced by LOOPSB_MERGE2_VARIANT, -1 = pick per call
   long long x_span_bytes = -1;   // loopsb_plan_hint_x_bytes: how much of x the matrix's columns touch
+  generic::state* cell = nullptr; // schedule::setup<>-driven cells without a reference kernel (spmv_generic.cu)
   int wo_grid = 0;   // work_oriented: reference-style grid (blocks of 128 threads)
   long long* phases = nullptr;  // LOOPSB_DEBUG_PHASES=1: per-CTA phase cycle counters
   int* carry_row = nullptr;
@@ -696,6 +707,7 @@ int loopsb_plan_destroy(loopsb_plan_t* plan) {
   if (plan->phases) cudaFree(plan->phases);
   if (plan->tc) bcsr_tc::destroy(plan->tc);
   if (plan->tiled) bt::destroy(plan->tiled);
+  if (plan->cell) generic::destroy(plan->cell);
   free_probes(plan);
   delete plan;
   return LOOPSB_OK;
@@ -728,6 +740,24 @@ int loopsb_plan_create(loopsb_plan_t** out, const loopsb_layout_t* lay,
   const int T = lay->num_tiles, A = lay->num_atoms;
 
   auto fail = [&](int code) { loopsb_plan_destroy(p); return code; };
+
+  if (generic::supports(lay->kind, schedule)) {
+    // coo x {group, work, merge}, ell x {group, work}: no kernel in the reference tree; the cell is
+    // the schedule's setup<> over that layout with the format's per-atom body
+    int g = 0;
+    if (schedule == LOOPSB_SCHED_WORK_ORIENTED) {
+      int rc = loopsb_work_oriented_grid(&g);
+      if (rc != LOOPSB_OK) return fail(rc);
+      p->wo_grid = g;
+    }
+    int rc = generic::create(&p->cell, lay, schedule, g, s);
+    if (rc != LOOPSB_OK) return fail(rc);
+    p->cta_threads = 128;
+    p->launches = 2;
+    p->grid = schedule == LOOPSB_SCHED_WORK_ORIENTED ? g : (T + 127) / 128;
+    *out = p;
+    return LOOPSB_OK;
+  }
 
   if (schedule == LOOPSB_SCHED_MERGE_PATH_FLAT) {
     const bool array_ends = lay->kind == LOOPSB_LAYOUT_CSR;
@@ -994,6 +1024,13 @@ int loopsb_spmv_f32(loopsb_plan_t* plan, const float* values,
   if (A == 0) {  // nothing stored: y = 0
     LOOPSB_CUDA_TRY(cudaMemsetAsync(y, 0, size_t(num_rows) * sizeof(float), s));
     return LOOPSB_OK;
+  }
+
+  if (plan->cell) {
+    probe_scope probe(plan, s);
+    const int rc = generic::run(plan->cell, &lay, plan->schedule, values, col_indices, row_indices, x, y, num_rows, s);
+    probe.close();
+    return rc;
   }
 
   switch (plan->schedule) {

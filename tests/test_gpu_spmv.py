@@ -275,13 +275,46 @@ def test_host_buffer_entry_point(oracle, battery):
 
 
 def test_unsupported_cells_fail_loudly():
-    from loops_b200 import _lib, coo_t, csr_t
-    from loops_b200.algorithms import spmv
+    from loops_b200 import _lib, csr_t
+    from loops_b200.container import csc_t
     off, idx, val = random_csr(10, 10, 0.3, 1)
-    coo = coo_t.from_csr(csr_t(10, 10, off, idx, val))
+    csc = csc_t.from_csr(csr_t(10, 10, off, idx, val))
     with pytest.raises(_lib.LoopsbError) as e:
-        coo.plan(_lib.SCHED_GROUP_MAPPED)
+        csc.plan(_lib.SCHED_GROUP_MAPPED)          # csc has only its thread_mapped entry point
     assert e.value.status == _lib.ERR_UNSUPPORTED
+
+
+def test_all_twelve_config3_cells(oracle, battery):
+    """BASELINE configs[2]: {thread_mapped, group_mapped, work_oriented, merge_path_flat} x
+    {csr, coo, ell}. Seven cells have a reference kernel; the other five (coo x group / work /
+    merge, ell x group / work) are schedule::setup<> over that layout with the format's
+    per-atom body. Every cell: exact on exact inputs, and within the north-star
+    tolerance on the battery's floats; COO cells also on row-unsorted triples."""
+    from loops_b200 import csr_t, coo_t, ell_t
+    from loops_b200.algorithms import spmv
+    assert len(spmv.CELLS) == 12
+    off, idx, val = random_csr(900, 700, 0.02, seed=17, exact=True, empty_every=5, heavy_row=(400, 650))
+    x = np.random.default_rng(6).integers(1, 11, 700).astype(np.float32)
+    ref = oracle.spmv(off, idx, val, x)
+    A = csr_t(900, 700, off, idx, val)
+    perm = np.random.default_rng(1).permutation(len(idx))
+    rows_of = np.repeat(np.arange(900, dtype=np.int32), np.diff(off))
+    containers = {"csr": [A], "coo": [coo_t.from_csr(A), coo_t(900, 700, rows_of[perm], idx[perm], val[perm])],
+                  "ell": [ell_t.from_csr(A)]}
+    xd = torch.as_tensor(x).cuda()
+    for (layout, sched), fn in spmv.CELLS.items():
+        for M in containers[layout]:
+            y = torch.full((900,), float("nan"), device="cuda")
+            fn(M, xd, y)
+            np.testing.assert_array_equal(y.cpu().numpy(), ref, err_msg=f"{layout} x {sched}")
+    for b in battery:
+        A = csr_t(b["rows"], b["cols"], b["off"], b["idx"], b["val"])
+        cs = {"csr": A, "coo": coo_t.from_csr(A), "ell": ell_t.from_csr(A)}
+        xb = torch.as_tensor(b["x"]).cuda()
+        for (layout, sched), fn in spmv.CELLS.items():
+            y = torch.full((b["rows"],), float("nan"), device="cuda")
+            fn(cs[layout], xb, y)
+            _assert_close(oracle, b["off"], b["idx"], b["val"], b["x"], y.cpu().numpy(), (layout, sched, b["name"]))
 
 
 def test_full_size_config2_properties(oracle):

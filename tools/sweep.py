@@ -1,7 +1,7 @@
 """tools/sweep.py -- BASELINE configs 3 and 4 on one B200:
   config 3: {thread_mapped, group_mapped, work_oriented, merge_path_flat} x
-            {csr, coo, ell} on the 2^20-row / 2^25-nnz synthetic matrix (cells
-            that have a kernel; the reference itself only ships 7 of the 12),
+            {csr, coo, ell} on the 2^20-row / 2^25-nnz synthetic matrix: all 12 cells
+            (the reference itself ships kernels for 7 of them),
   config 4: BCSR 4x4 bf16 on tcgen05, 262,144 block-rows / 8,388,608 blocks,
 and, for context, the reference's own kernels (oracle/_ref/libloopsref_gpu.so,
 built from its unmodified headers with -DLOOPS_TARGET_ARCH=100) on the same box.
@@ -63,15 +63,17 @@ def main():
         print(f"{layout:4s} {sched:16s} {med*1e3:9.1f} us  {nnz/med/1e6:7.1f} Gnnz/s  {nbytes/med/1e6:7.0f} GB/s  ok={ok}",
               file=sys.stderr)
 
-    for name in ("merge_path_flat", "work_oriented", "group_mapped", "thread_mapped"):
-        cell("csr", name, spmv.BY_NAME[name], A, bytes_csr)
+    scheds = ("merge_path_flat", "work_oriented", "group_mapped", "thread_mapped")
+    for name in scheds:
+        cell("csr", name, spmv.CELLS[("csr", name)], A, bytes_csr)
     coo = csr_to_coo_device(A)
-    cell("coo", "thread_mapped", spmv.coo_thread_mapped, coo, bytes_coo)
+    for name in scheds:
+        cell("coo", name, spmv.CELLS[("coo", name)], coo, bytes_coo)
     ell = csr_to_ell_device(A)
     bytes_ell = rows * ell.pitch * 8 + cols * 4 + rows * 4
     out["ell_pitch"] = ell.pitch
-    cell("ell", "thread_mapped", spmv.ell_thread_mapped, ell, bytes_ell)
-    cell("ell", "merge_path_flat", spmv.ell_merge_path, ell, bytes_ell)
+    for name in scheds:
+        cell("ell", name, spmv.CELLS[("ell", name)], ell, bytes_ell)
     del ell, coo
     torch.cuda.empty_cache()
 
