@@ -110,6 +110,20 @@ int loopsb_plan_create(loopsb_plan_t** out, const loopsb_layout_t* lay,
                        int schedule, void* stream);
 int loopsb_plan_destroy(loopsb_plan_t* plan);
 int loopsb_plan_info(const loopsb_plan_t* plan, loopsb_plan_info_t* info);
+/* STALENESS CONTRACT of plan-owned copies. Two optional accelerators keep a re-ordered COPY
+ * of the matrix inside the plan (loopsb_plan_tile_csr: indices + values; loopsb_plan_pack_bcsr4x4:
+ * block values + block columns). They are keyed by the caller's array ADDRESSES, so a change of
+ * the arrays' CONTENTS in place cannot be seen by the library. After such a change call
+ * loopsb_plan_invalidate: it drops every copy, SpMV calls on the plan then run the kernels
+ * that read the live arrays (always correct), and the copy can be rebuilt with another
+ * loopsb_plan_tile_csr / loopsb_plan_pack_bcsr4x4 when the values have settled. Plans WITHOUT
+ * such a copy never hold matrix values. (The Python mirror tracks torch's in-place version
+ * counters and calls this by itself; the C++ mirror exposes csr.values_changed().) */
+int loopsb_plan_invalidate(loopsb_plan_t* plan);
+/* How many SpMV calls it takes for loopsb_plan_tile_csr to pay for itself on this matrix
+ * (build time / per-call saving, from rates measured on B200); -1 = never (the cost model
+ * declines the matrix). The C++ mirror tiles a cached plan once that many calls were made. */
+int loopsb_plan_tile_breakeven(const loopsb_plan_t* plan, int32_t num_cols, int64_t* calls);
 /* Tuning hint: the number of bytes of x the matrix's columns range over when that is
  * less than num_cols * sizeof(value) (a column block of a larger matrix). Only the launch
  * geometry depends on it (resident CTAs per SM vs L1 capacity), never the result. */

@@ -92,6 +92,8 @@ SIGNATURES = {
     "loopsb_plan_destroy": (C.c_int, [_P]),
     "loopsb_plan_info": (C.c_int, [_P, C.POINTER(PlanInfo)]),
     "loopsb_plan_hint_x_bytes": (C.c_int, [_P, C.c_int64]),
+    "loopsb_plan_invalidate": (C.c_int, [_P]),
+    "loopsb_plan_tile_breakeven": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int64)]),
     "loopsb_plan_merge_coords_host": (C.c_int, [_P, _P, C.c_int64]),
     "loopsb_plan_debug_phases_host": (C.c_int, [_P, _P, C.c_int64]),
     "loopsb_plan_probe_begin": (C.c_int, [_P, C.c_int32]),

@@ -76,6 +76,25 @@ class csr_t(_planned):
         p = super().plan(schedule, stream)
         if schedule != _lib.SCHED_MERGE_PATH_FLAT or not self.values.is_cuda or self.nnzs == 0:
             return p
+        # Staleness guard: the tiled copy is keyed by array addresses, torch counts in-place
+        # writes. If values / indices were written since the copy was made, drop it now (the
+        # plain kernel reads the live arrays) and re-tile only once a call sees the same
+        # version twice in a row -- a one-off update pays one re-tile, a matrix whose values
+        # change every iteration never does.
+        ver = (self.indices._version, self.values._version, self.indices.data_ptr(), self.values.data_ptr())
+        if getattr(p, "_tile_state", None) in ("forced", "auto") and getattr(p, "_tile_ver", ver) != ver:
+            p.invalidate()
+            p._tile_state = "stale"
+            p._tile_ver = ver
+            p._stale_reason = "values or column ids were modified in place after tiling"
+            if tiled is None or tiled == "auto":
+                return p
+        elif getattr(p, "_tile_state", None) == "stale":
+            if getattr(p, "_tile_ver", None) != ver:
+                p._tile_ver = ver                      # still changing: stay on the plain kernel
+                if tiled is not True:
+                    return p
+            p._tile_state = None                       # settled (or forced): tile again below
         if tiled is None:
             env = os.environ.get("LOOPSB_TILED", "auto")
             tiled = {"0": False, "1": True}.get(env, "auto")
@@ -87,7 +106,18 @@ class csr_t(_planned):
         elif state != ("forced" if tiled is True else "auto") and not (state == "forced" and tiled == "auto"):
             p.tile_csr(self.indices, self.values, self.cols, force=(tiled is True), stream=stream)
             p._tile_state = "forced" if tiled is True else "auto"
+            p._tile_ver = ver
         return p
+
+    def values_changed(self):
+        """Tell every cached plan that values / column ids were changed in place (what the
+        version check in ``plan`` does by itself for torch in-place ops; needed only when the
+        arrays were written behind torch's back, e.g. by a raw CUDA kernel)."""
+        for p in self._plans.values():
+            p.invalidate()
+            if getattr(p, "_tile_state", None) in ("forced", "auto"):
+                p._tile_state = "stale"
+                p._tile_ver = None
 
     def host(self):
         return (self.offsets.cpu().numpy(), self.indices.cpu().numpy(), self.values.cpu().numpy())

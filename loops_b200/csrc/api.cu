@@ -925,6 +925,36 @@ int loopsb_plan_create(loopsb_plan_t** out, const loopsb_layout_t* lay,
   return LOOPSB_OK;
 }
 
+int loopsb_plan_invalidate(loopsb_plan_t* plan) {
+  LOOPSB_REQUIRE(plan != nullptr, "plan is null");
+  // the caller changed values / column ids IN PLACE: every plan-owned copy of them is stale.
+  // Dropping them is always safe -- SpMV calls fall back to the kernels that read the live arrays.
+  if (plan->tiled) { bt::destroy(plan->tiled); plan->tiled = nullptr; }
+  if (plan->tc) bcsr_tc::unpack(plan->tc);
+  return LOOPSB_OK;
+}
+
+int loopsb_plan_tile_breakeven(const loopsb_plan_t* plan, int32_t num_cols, int64_t* calls) {
+  LOOPSB_REQUIRE(plan != nullptr && calls != nullptr, "null argument");
+  *calls = -1;
+  if (plan->schedule != LOOPSB_SCHED_MERGE_PATH_FLAT || plan->lay.kind != LOOPSB_LAYOUT_CSR) return LOOPSB_OK;
+  const device_props* dp = current_device();
+  if (!dp) return LOOPSB_ERR_CUDA;
+  const double nnz = double(plan->lay.num_atoms), rows = double(plan->lay.num_tiles);
+  if (nnz < double(1 << 22) || rows == 0 || num_cols <= 0) return LOOPSB_OK;
+  bt::geom g = bt::choose_geom(plan->lay.num_tiles, num_cols, dp->sm_count, dp->max_smem_optin);
+  const char* why = "";
+  if (!bt::derive(g, plan->lay.num_tiles, num_cols, &why)) return LOOPSB_OK;
+  if (double(g.nb) * double(num_cols) * 4.0 > nnz * 8.0) return LOOPSB_OK;      // the cost model would decline
+  // Measured on B200 (profiles/): device build ~2.2 ns per nonzero + ~20 ms fixed; plain CSR kernel
+  // ~205 Gnnz/s; band-tiled kernel ~4.6 TB/s of its 8.4 B per nonzero.
+  const double build_s = 0.020 + 2.2e-9 * nnz;
+  const double plain_s = nnz / 205e9, tiled_s = nnz * 8.4 / 4.6e12;
+  if (plain_s <= tiled_s) return LOOPSB_OK;
+  *calls = int64_t(build_s / (plain_s - tiled_s)) + 1;
+  return LOOPSB_OK;
+}
+
 int loopsb_plan_hint_x_bytes(loopsb_plan_t* plan, int64_t bytes) {
   LOOPSB_REQUIRE(plan != nullptr, "plan is null");
   plan->x_span_bytes = bytes;

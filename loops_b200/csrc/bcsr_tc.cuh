@@ -613,6 +613,12 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // Build (or rebuild) the packed copy from `values`. One pass over the blocks.
+// Forget the packed copy (the caller changed the block values in place): SpMV calls take the
+// direct kernel, which reads the live arrays, until pack() is called again.
+inline void unpack(plan_data* p) {
+  if (p) p->packed_key = nullptr;
+}
+
 inline int pack(plan_data* p, const uint16_t* values, const int* block_cols, cudaStream_t stream) {
   LOOPSB_REQUIRE(p != nullptr, "null plan");
   if (p->num_items == 0) { p->packed_key = values; return LOOPSB_OK; }

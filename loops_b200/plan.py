@@ -48,6 +48,19 @@ class Plan:
         self._tiled_keep = (indices, values)   # the copy is keyed by these pointers
         return True
 
+    def invalidate(self):
+        """The matrix values / column ids were changed in place: drop every plan-owned copy of
+        them (``loopsb_plan_invalidate``); SpMV calls read the live arrays from now on."""
+        _lib.check(self._lib.loopsb_plan_invalidate(self.handle), "loopsb_plan_invalidate")
+        self._tiled_keep = None
+        self._packed_key = None
+
+    def tile_breakeven(self, cols: int) -> int:
+        """SpMV calls after which tiling has paid for itself (-1 = never)."""
+        n = C.c_int64(-1)
+        _lib.check(self._lib.loopsb_plan_tile_breakeven(self.handle, int(cols), C.byref(n)), "loopsb_plan_tile_breakeven")
+        return int(n.value)
+
     def untile(self):
         _lib.check(self._lib.loopsb_plan_untile(self.handle), "loopsb_plan_untile")
         self._tiled_keep = None
