@@ -16,6 +16,8 @@
  */
 #pragma once
 
+#include <cstdlib>
+
 #include <cuda_runtime.h>
 
 #include <loops/error.hxx>
@@ -45,26 +47,98 @@ struct plan_guard {
 template <typename vec_t>
 auto* raw(vec_t& v) { return thrust::raw_pointer_cast(v.data()); }
 
-inline util::timer_t run(const loopsb_layout_t& lay, int schedule, const float* values,
-                         const int* cols, const int* rows_idx, const float* x, float* y,
-                         std::size_t nrows, std::size_t ncols, cudaStream_t stream) {
+/// One SpMV through the plan cached on the container (created on the first call). `k_rows` is
+/// the third array the plan's validity hangs on (CSR offsets / COO row ids / null for ELL).
+inline util::timer_t run(::loops::detail::plan_cache_t& cache, const loopsb_layout_t& lay, int schedule,
+                         const float* values, const int* cols, const int* rows_idx, const void* k_rows,
+                         const float* x, float* y, std::size_t nrows, std::size_t ncols, std::size_t nnzs,
+                         cudaStream_t stream) {
+  auto& e = cache.get(schedule, lay, k_rows, cols, values, nrows, ncols, nnzs, std::size_t(lay.pitch), stream);
+  util::timer_t timer(stream);
+  timer.start();
+  error::throw_if_status(loopsb_spmv_f32(e.plan, values, cols, rows_idx, x, y, static_cast<int32_t>(nrows),
+                                         static_cast<int32_t>(ncols), stream),
+                         "loopsb_spmv_f32");
+  cudaStreamSynchronize(stream);
+  timer.stop();
+  ++e.calls;
+  return timer;
+}
+
+/// LOOPSB_TILED: "0" = the cached merge_path_flat plan never takes a band-tiled copy of the matrix,
+/// "1" = on the first call, anything else / unset = once the calls made on the plan reach the
+/// break-even count of loopsb_plan_tile_breakeven (build time / per-call saving on B200).
+/// One SpMV on a plan made for this call only (layout views that are not cached on a container).
+inline util::timer_t run_once(const loopsb_layout_t& lay, int schedule, const float* values, const int* cols,
+                              const int* rows_idx, const float* x, float* y, std::size_t nrows, std::size_t ncols,
+                              cudaStream_t stream) {
   plan_guard plan(lay, schedule, stream);
   util::timer_t timer(stream);
   timer.start();
-  error::throw_if_status(loopsb_spmv_f32(plan.p, values, cols, rows_idx, x, y,
-                                         static_cast<int32_t>(nrows), static_cast<int32_t>(ncols), stream),
+  error::throw_if_status(loopsb_spmv_f32(plan.p, values, cols, rows_idx, x, y, static_cast<int32_t>(nrows),
+                                         static_cast<int32_t>(ncols), stream),
                          "loopsb_spmv_f32");
   cudaStreamSynchronize(stream);
   timer.stop();
   return timer;
 }
 
+inline util::timer_t run_coo(coo_t<int, float>& coo, int schedule, vector_t<float>& x, vector_t<float>& y,
+                             cudaStream_t stream) {
+  layout::coo<int, int> lay(static_cast<int>(coo.nnzs));
+  return run(coo.plans(), lay.descriptor(), schedule, raw(coo.values), raw(coo.col_indices), raw(coo.row_indices),
+             raw(coo.row_indices), raw(x), raw(y), coo.rows, coo.cols, coo.nnzs, stream);
+}
+
+inline util::timer_t run_ell(ell_t<int, float>& ell, int schedule, vector_t<float>& x, vector_t<float>& y,
+                             cudaStream_t stream) {
+  return run(ell.plans(), ell.layout().descriptor(), schedule, raw(ell.values), raw(ell.indices), nullptr, nullptr,
+             raw(x), raw(y), ell.rows, ell.cols, ell.nnzs, stream);
+}
+
+inline int tiling_mode() {
+  const char* e = std::getenv("LOOPSB_TILED");
+  if (e && e[0] == '0' && e[1] == 0) return 0;
+  if (e && e[0] == '1' && e[1] == 0) return 1;
+  return 2;
+}
+
 }  // namespace detail
 
+/**
+ * reference algorithms/spmv/merge_path_flat.cuh:96-139. The plan (merge-path coordinates) is
+ * cached on `csr` (container/formats.hxx: detail::plan_cache_t), so calls after the first
+ * allocate nothing; once the calls made on it reach the break-even count of the band-tiled
+ * copy (loopsb_plan_tile_breakeven; LOOPSB_TILED=1 or csr.plans().tiling = 1: at once, 0: never) the plan takes that copy
+ * and later calls run the band-tiled kernel. The copy holds VALUES: after writing csr.values /
+ * csr.indices in place call csr.values_changed(), after writing csr.offsets in place
+ * csr.structure_changed(); re-assigned arrays are noticed by themselves.
+ */
 inline util::timer_t merge_path_flat(csr_t<int, int, float>& csr, vector_t<float>& x,
                                      vector_t<float>& y, cudaStream_t stream = 0) {
-  return detail::run(csr.layout().descriptor(), LOOPSB_SCHED_MERGE_PATH_FLAT, detail::raw(csr.values),
-                     detail::raw(csr.indices), nullptr, detail::raw(x), detail::raw(y), csr.rows, csr.cols, stream);
+  const loopsb_layout_t lay = csr.layout().descriptor();
+  const float* values = detail::raw(csr.values);
+  const int* indices = detail::raw(csr.indices);
+  auto& e = csr.plans().get(LOOPSB_SCHED_MERGE_PATH_FLAT, lay, detail::raw(csr.offsets), indices, values, csr.rows,
+                            csr.cols, csr.nnzs, std::size_t(lay.pitch), stream);
+  const int mode = csr.plans().tiling >= 0 ? csr.plans().tiling : detail::tiling_mode();
+  if (!e.tiled && mode != 0 && e.tile_after != -1 && csr.nnzs > 0) {
+    if (e.tile_after == -2) {
+      int64_t n = -1;
+      error::throw_if_status(loopsb_plan_tile_breakeven(e.plan, static_cast<int32_t>(csr.cols), &n),
+                             "loopsb_plan_tile_breakeven");
+      e.tile_after = mode == 1 ? 0 : static_cast<long long>(n);
+    }
+    if (e.tile_after >= 0 && e.calls >= e.tile_after) {
+      const int rc = loopsb_plan_tile_csr(e.plan, indices, values, static_cast<int32_t>(csr.cols),
+                                          mode == 1 ? LOOPSB_TILE_FORCE : 0, stream);
+      if (rc != LOOPSB_OK && rc != LOOPSB_ERR_UNSUPPORTED) error::throw_if_status(rc, "loopsb_plan_tile_csr");
+      e.tiled = rc == LOOPSB_OK;
+      if (!e.tiled) e.tile_after = -1;   // declined: do not ask again for these arrays
+    }
+  }
+  return detail::run(csr.plans(), lay, LOOPSB_SCHED_MERGE_PATH_FLAT, values, indices, nullptr,
+                     detail::raw(csr.offsets), detail::raw(x), detail::raw(y), csr.rows, csr.cols, csr.nnzs, stream);
 }
 
 /**
@@ -114,41 +188,38 @@ class merge_path_plan_t {
 
 inline void work_oriented(csr_t<int, int, float>& csr, vector_t<float>& x, vector_t<float>& y,
                           cudaStream_t stream = 0) {
-  detail::run(csr.layout().descriptor(), LOOPSB_SCHED_WORK_ORIENTED, detail::raw(csr.values),
-              detail::raw(csr.indices), nullptr, detail::raw(x), detail::raw(y), csr.rows, csr.cols, stream);
+  detail::run(csr.plans(), csr.layout().descriptor(), LOOPSB_SCHED_WORK_ORIENTED, detail::raw(csr.values),
+              detail::raw(csr.indices), nullptr, detail::raw(csr.offsets), detail::raw(x), detail::raw(y), csr.rows,
+              csr.cols, csr.nnzs, stream);
 }
 
 inline void thread_mapped(csr_t<int, int, float>& csr, vector_t<float>& x, vector_t<float>& y,
                           cudaStream_t stream = 0) {
-  detail::run(csr.layout().descriptor(), LOOPSB_SCHED_THREAD_MAPPED, detail::raw(csr.values),
-              detail::raw(csr.indices), nullptr, detail::raw(x), detail::raw(y), csr.rows, csr.cols, stream);
+  detail::run(csr.plans(), csr.layout().descriptor(), LOOPSB_SCHED_THREAD_MAPPED, detail::raw(csr.values),
+              detail::raw(csr.indices), nullptr, detail::raw(csr.offsets), detail::raw(x), detail::raw(y), csr.rows,
+              csr.cols, csr.nnzs, stream);
 }
 
 inline void group_mapped(csr_t<int, int, float>& csr, vector_t<float>& x, vector_t<float>& y,
                          cudaStream_t stream = 0) {
-  detail::run(csr.layout().descriptor(), LOOPSB_SCHED_GROUP_MAPPED, detail::raw(csr.values),
-              detail::raw(csr.indices), nullptr, detail::raw(x), detail::raw(y), csr.rows, csr.cols, stream);
+  detail::run(csr.plans(), csr.layout().descriptor(), LOOPSB_SCHED_GROUP_MAPPED, detail::raw(csr.values),
+              detail::raw(csr.indices), nullptr, detail::raw(csr.offsets), detail::raw(x), detail::raw(y), csr.rows,
+              csr.cols, csr.nnzs, stream);
 }
 
 inline util::timer_t coo_thread_mapped(coo_t<int, float>& coo, vector_t<float>& x, vector_t<float>& y,
                                        cudaStream_t stream = 0) {
-  layout::coo<int, int> lay(static_cast<int>(coo.nnzs));
-  return detail::run(lay.descriptor(), LOOPSB_SCHED_THREAD_MAPPED, detail::raw(coo.values),
-                     detail::raw(coo.col_indices), detail::raw(coo.row_indices), detail::raw(x),
-                     detail::raw(y), coo.rows, coo.cols, stream);
+  return detail::run_coo(coo, LOOPSB_SCHED_THREAD_MAPPED, x, y, stream);
 }
 
 inline void ell_thread_mapped(ell_t<int, float>& ell, vector_t<float>& x, vector_t<float>& y,
                               cudaStream_t stream = 0) {
-  detail::run(ell.layout().descriptor(), LOOPSB_SCHED_THREAD_MAPPED, detail::raw(ell.values),
-              detail::raw(ell.indices), nullptr, detail::raw(x), detail::raw(y), ell.rows, ell.cols, stream);
+  detail::run_ell(ell, LOOPSB_SCHED_THREAD_MAPPED, x, y, stream);
 }
 
 inline util::timer_t ell_merge_path(ell_t<int, float>& ell, vector_t<float>& x, vector_t<float>& y,
                                     cudaStream_t stream = 0) {
-  return detail::run(ell.layout().descriptor(), LOOPSB_SCHED_MERGE_PATH_FLAT, detail::raw(ell.values),
-                     detail::raw(ell.indices), nullptr, detail::raw(x), detail::raw(y), ell.rows, ell.cols,
-                     stream);
+  return detail::run_ell(ell, LOOPSB_SCHED_MERGE_PATH_FLAT, x, y, stream);
 }
 
 // ---- the five (schedule x layout) cells of BASELINE configs[2] the reference has no kernel for:
@@ -156,32 +227,23 @@ inline util::timer_t ell_merge_path(ell_t<int, float>& ell, vector_t<float>& x, 
 // (loops_b200/csrc/spmv_generic.cu). New entry points, same argument meaning. ----
 inline util::timer_t coo_group_mapped(coo_t<int, float>& coo, vector_t<float>& x, vector_t<float>& y,
                                       cudaStream_t stream = 0) {
-  layout::coo<int, int> lay(static_cast<int>(coo.nnzs));
-  return detail::run(lay.descriptor(), LOOPSB_SCHED_GROUP_MAPPED, detail::raw(coo.values), detail::raw(coo.col_indices),
-                     detail::raw(coo.row_indices), detail::raw(x), detail::raw(y), coo.rows, coo.cols, stream);
+  return detail::run_coo(coo, LOOPSB_SCHED_GROUP_MAPPED, x, y, stream);
 }
 inline util::timer_t coo_work_oriented(coo_t<int, float>& coo, vector_t<float>& x, vector_t<float>& y,
                                        cudaStream_t stream = 0) {
-  layout::coo<int, int> lay(static_cast<int>(coo.nnzs));
-  return detail::run(lay.descriptor(), LOOPSB_SCHED_WORK_ORIENTED, detail::raw(coo.values), detail::raw(coo.col_indices),
-                     detail::raw(coo.row_indices), detail::raw(x), detail::raw(y), coo.rows, coo.cols, stream);
+  return detail::run_coo(coo, LOOPSB_SCHED_WORK_ORIENTED, x, y, stream);
 }
 inline util::timer_t coo_merge_path(coo_t<int, float>& coo, vector_t<float>& x, vector_t<float>& y,
                                     cudaStream_t stream = 0) {
-  layout::coo<int, int> lay(static_cast<int>(coo.nnzs));
-  return detail::run(lay.descriptor(), LOOPSB_SCHED_MERGE_PATH_FLAT, detail::raw(coo.values),
-                     detail::raw(coo.col_indices), detail::raw(coo.row_indices), detail::raw(x), detail::raw(y),
-                     coo.rows, coo.cols, stream);
+  return detail::run_coo(coo, LOOPSB_SCHED_MERGE_PATH_FLAT, x, y, stream);
 }
 inline util::timer_t ell_group_mapped(ell_t<int, float>& ell, vector_t<float>& x, vector_t<float>& y,
                                       cudaStream_t stream = 0) {
-  return detail::run(ell.layout().descriptor(), LOOPSB_SCHED_GROUP_MAPPED, detail::raw(ell.values),
-                     detail::raw(ell.indices), nullptr, detail::raw(x), detail::raw(y), ell.rows, ell.cols, stream);
+  return detail::run_ell(ell, LOOPSB_SCHED_GROUP_MAPPED, x, y, stream);
 }
 inline util::timer_t ell_work_oriented(ell_t<int, float>& ell, vector_t<float>& x, vector_t<float>& y,
                                        cudaStream_t stream = 0) {
-  return detail::run(ell.layout().descriptor(), LOOPSB_SCHED_WORK_ORIENTED, detail::raw(ell.values),
-                     detail::raw(ell.indices), nullptr, detail::raw(x), detail::raw(y), ell.rows, ell.cols, stream);
+  return detail::run_ell(ell, LOOPSB_SCHED_WORK_ORIENTED, x, y, stream);
 }
 
 /// reference algorithms/spmv/original.cuh:55-72 -- the plain one-thread-per-row kernel; same
@@ -194,7 +256,7 @@ inline void original(csr_t<int, int, float>& csr, vector_t<float>& x, vector_t<f
 /// reference algorithms/spmv/csc_thread_mapped.cuh:54-84 (one thread per column, atomics into y).
 inline util::timer_t csc_thread_mapped(csc_t<int, int, float>& csc, vector_t<float>& x, vector_t<float>& y,
                                        cudaStream_t stream = 0) {
-  return detail::run(csc.layout().descriptor(), LOOPSB_SCHED_THREAD_MAPPED, detail::raw(csc.values),
+  return detail::run_once(csc.layout().descriptor(), LOOPSB_SCHED_THREAD_MAPPED, detail::raw(csc.values),
                      detail::raw(csc.indices), nullptr, detail::raw(x), detail::raw(y), csc.rows, csc.cols, stream);
 }
 
@@ -220,8 +282,8 @@ template <std::size_t K = 8>
 util::timer_t flat_partitioned(csr_t<int, int, float>& csr, vector_t<float>& x, vector_t<float>& y,
                                cudaStream_t stream = 0) {
   layout::flat_uniform_occupancy<K, layout::csr<int, int>> lay(csr.layout());
-  return detail::run(lay.descriptor(), LOOPSB_SCHED_THREAD_MAPPED, detail::raw(csr.values),
-                     detail::raw(csr.indices), nullptr, detail::raw(x), detail::raw(y), csr.rows, csr.cols, stream);
+  return detail::run_once(lay.descriptor(), LOOPSB_SCHED_THREAD_MAPPED, detail::raw(csr.values), detail::raw(csr.indices),
+                          nullptr, detail::raw(x), detail::raw(y), csr.rows, csr.cols, stream);
 }
 
 template <std::size_t R, std::size_t C>

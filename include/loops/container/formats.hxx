@@ -17,6 +17,8 @@
 
 #include <type_traits>
 
+#include <cuda_runtime.h>
+
 #include <loops/container/vector.hxx>
 #include <loops/container/layout.hxx>
 #include <loops/error.hxx>
@@ -36,6 +38,95 @@ template <typename vec_t>
 auto* raw(vec_t& v) { return thrust::raw_pointer_cast(v.data()); }
 template <typename vec_t>
 const auto* raw(const vec_t& v) { return thrust::raw_pointer_cast(v.data()); }
+}  // namespace detail
+
+namespace detail {
+/**
+ * Plans kept on a container between SpMV calls. The reference runs its per-matrix
+ * preprocess inside every algorithms::spmv::* call (merge_path_flat.cuh:111,
+ * schedule/merge_path_flat.hxx:92-172: allocate + search + free, each call); here the first
+ * call on a container creates the plan and later calls re-use it, so the steady state has
+ * no allocation and no search. Entries are keyed by the ADDRESSES and sizes of the
+ * container's arrays: re-assigning an array (csr.values = other) is seen and rebuilds the
+ * plan; a change of the arrays' CONTENTS in place cannot be seen from the host -- call
+ * values_changed() (values / column ids) or structure_changed() (offsets, row ids) on the
+ * container after such a write. A plan never survives a copy of its container.
+ * Not thread-safe per container (like the thrust vectors beside it).
+ */
+class plan_cache_t {
+ public:
+  struct entry {
+    loopsb_plan_t* plan = nullptr;
+    int schedule = -1;
+    const void* key[3] = {nullptr, nullptr, nullptr};
+    std::size_t dims[4] = {0, 0, 0, 0};
+    long long calls = 0;         ///< SpMV calls since the plan was made / last invalidated
+    long long tile_after = -2;   ///< -2 not asked yet, -1 never, else calls after which a band-tiled copy pays
+    bool tiled = false;          ///< the plan holds a band-tiled copy of the matrix (loopsb_plan_tile_csr)
+  };
+
+  /// merge_path_flat on CSR: -1 = follow LOOPSB_TILED (default: after the break-even number of
+  /// calls), 0 = never take a band-tiled copy, 1 = on the next call, 2 = after break-even.
+  int tiling = -1;
+
+  plan_cache_t() = default;
+  plan_cache_t(const plan_cache_t& rhs) : tiling(rhs.tiling) {}
+  plan_cache_t& operator=(const plan_cache_t& rhs) {
+    if (this != &rhs) {
+      clear();
+      tiling = rhs.tiling;
+    }
+    return *this;
+  }
+  ~plan_cache_t() { clear(); }
+
+  /// The plan of `schedule` over these arrays, created on the first call (and again after the arrays moved).
+  entry& get(int schedule, const loopsb_layout_t& lay, const void* k0, const void* k1, const void* k2,
+             std::size_t d0, std::size_t d1, std::size_t d2, std::size_t d3, cudaStream_t stream) {
+    entry* slot = nullptr;
+    for (auto& e : entries_)
+      if (e.schedule == schedule) slot = &e;
+    if (slot && slot->plan && slot->key[0] == k0 && slot->key[1] == k1 && slot->key[2] == k2 &&
+        slot->dims[0] == d0 && slot->dims[1] == d1 && slot->dims[2] == d2 && slot->dims[3] == d3)
+      return *slot;
+    if (!slot) {
+      entries_.emplace_back();
+      slot = &entries_.back();
+    }
+    if (slot->plan) loopsb_plan_destroy(slot->plan);
+    *slot = entry();
+    slot->schedule = schedule;
+    error::throw_if_status(loopsb_plan_create(&slot->plan, &lay, schedule, stream), "loopsb_plan_create");
+    slot->key[0] = k0; slot->key[1] = k1; slot->key[2] = k2;
+    slot->dims[0] = d0; slot->dims[1] = d1; slot->dims[2] = d2; slot->dims[3] = d3;
+    return *slot;
+  }
+
+  /// Values / column ids were written in place: drop every plan-owned copy of them
+  /// (loopsb_plan_invalidate); the plans themselves (built from the offsets) stay.
+  void values_changed() {
+    for (auto& e : entries_) {
+      if (e.plan) loopsb_plan_invalidate(e.plan);
+      e.tiled = false;
+      e.calls = 0;
+    }
+  }
+  /// Offsets / row ids were written in place: every plan is void.
+  void clear() {
+    for (auto& e : entries_)
+      if (e.plan) loopsb_plan_destroy(e.plan);
+    entries_.clear();
+  }
+  std::size_t size() const { return entries_.size(); }
+  const entry* find(int schedule) const {
+    for (auto& e : entries_)
+      if (e.schedule == schedule) return &e;
+    return nullptr;
+  }
+
+ private:
+  std::vector<entry> entries_;
+};
 }  // namespace detail
 
 template <typename index_t, typename value_t, memory_space_t space = memory_space_t::device>
@@ -86,9 +177,16 @@ struct coo_t {
     r.resize(kept); c.resize(kept); v.resize(kept);
     nnzs = kept;
     row_indices = r; col_indices = c; values = v;
+    plans_.clear();
   }
 
+  /// In-place writes to the arrays (see detail::plan_cache_t): the cached SpMV plans are rebuilt.
+  void values_changed() { plans_.values_changed(); }
+  void structure_changed() { plans_.clear(); }
+  detail::plan_cache_t& plans() const { return plans_; }
+
  private:
+  mutable detail::plan_cache_t plans_;
   void reorder(bool by_row) {
     thrust::host_vector<index_t> r(row_indices), c(col_indices);
     thrust::host_vector<value_t> v(values);
@@ -105,6 +203,7 @@ struct coo_t {
       r2[i] = r[perm[i]]; c2[i] = c[perm[i]]; v2[i] = v[perm[i]];
     }
     row_indices = r2; col_indices = c2; values = v2;
+    plans_.clear();
   }
 };
 
@@ -155,6 +254,17 @@ struct csr_t {
         thrust::raw_pointer_cast(offsets.data()), static_cast<index_t>(rows),
         static_cast<offset_t>(nnzs));
   }
+
+  /// Call after writing `values` / `indices` IN PLACE (a kernel, thrust::transform, values[i] = ...):
+  /// the SpMV plans cached on this container drop their re-ordered copies of the matrix
+  /// (detail::plan_cache_t above). Re-assigning a whole array needs no call.
+  void values_changed() { plans_.values_changed(); }
+  /// Call after writing `offsets` in place: every cached plan is rebuilt on its next use.
+  void structure_changed() { plans_.clear(); }
+  detail::plan_cache_t& plans() const { return plans_; }
+
+ private:
+  mutable detail::plan_cache_t plans_;
 };
 
 template <typename index_t, typename value_t, memory_space_t space>
@@ -241,6 +351,14 @@ struct ell_t {
   layout::ell<index_t, index_t> layout() const {
     return layout::ell<index_t, index_t>(static_cast<index_t>(rows), static_cast<index_t>(pitch));
   }
+
+  /// In-place writes to the arrays (see detail::plan_cache_t). ELL plans depend on rows and pitch only.
+  void values_changed() { plans_.values_changed(); }
+  void structure_changed() { plans_.clear(); }
+  detail::plan_cache_t& plans() const { return plans_; }
+
+ private:
+  mutable detail::plan_cache_t plans_;
 };
 
 /// BCSR: R x C dense blocks, values[b*R*C + i*C + j]; block columns ascending

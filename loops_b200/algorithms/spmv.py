@@ -160,8 +160,9 @@ def dia_thread_mapped(dia: dia_t, x, y, stream=None, sync=True):
 def bcsr_thread_mapped(bcsr: bcsr_t, x, y, stream=None, sync=True, repack=False):
     """fp32 blocks: one thread per block-row (the reference kernel's map).
     bf16 4x4 blocks: the tcgen05 tensor-core kernel (BASELINE config 4); its plan
-    keeps a packed copy of the blocks (made on the first call; pass ``repack=True``
-    after changing ``bcsr.values`` / ``block_col_indices`` in place).
+    keeps a packed copy of the blocks (made on the first call and re-made when torch's
+    version counters show an in-place write to ``bcsr.values`` / ``block_col_indices``;
+    pass ``repack=True`` after a write torch cannot see, e.g. from a raw CUDA kernel).
     ``x`` must already be padded to ``num_block_cols * C`` (bcsr.padded_x)."""
     lib = _lib.load()
     stream = stream or torch.cuda.current_stream()
@@ -187,12 +188,15 @@ def bcsr_thread_mapped(bcsr: bcsr_t, x, y, stream=None, sync=True, repack=False)
         # once per matrix: the plan's packed copy of the block values (TMA-fed A tiles);
         # LOOPSB_BCSR_PACKED=0 keeps the kernel that reads the BCSR value array directly
         import os
+        # (re-made by itself when torch saw an in-place write to the arrays since the last pack)
+        key = (bcsr.values.data_ptr(), bcsr.values._version, bcsr.block_col_indices.data_ptr(),
+               bcsr.block_col_indices._version)
         if os.environ.get("LOOPSB_BCSR_PACKED", "1") != "0" and \
-                (repack or getattr(plan, "_packed_key", None) != bcsr.values.data_ptr()):
+                (repack or getattr(plan, "_packed_key", None) != key):
             _lib.check(lib.loopsb_plan_pack_bcsr4x4(plan.handle, _lib.ptr(bcsr.values),
                                                     _lib.ptr(bcsr.block_col_indices), _lib.stream_ptr(stream)),
                        "loopsb_plan_pack_bcsr4x4")
-            plan._packed_key = bcsr.values.data_ptr()
+            plan._packed_key = key
         _lib.check(lib.loopsb_spmv_bcsr4x4_bf16(plan.handle, _lib.ptr(bcsr.values),
                                                 _lib.ptr(bcsr.block_col_indices), _lib.ptr(x),
                                                 _lib.ptr(y), bcsr.rows, _lib.stream_ptr(stream)),

@@ -24,6 +24,9 @@
 #include <loops/algorithms/spmv/original.cuh>
 #include <loops/algorithms/spmm/thread_mapped.cuh>
 
+#include <thrust/fill.h>
+#include <thrust/transform.h>
+
 #include <cmath>
 #include <cstdio>
 #include <random>
@@ -85,6 +88,9 @@ __global__ void __launch_bounds__(int(TPB))
   }
 }
 
+struct twice_fn { __host__ __device__ float operator()(float v) const { return 2.0f * v; } };
+struct halve_fn { __host__ __device__ float operator()(float v) const { return 0.5f * v; } };
+
 static int failures = 0;
 static void check(const char* name, const thrust::host_vector<float>& y, const std::vector<float>& ref) {
   double worst = 0;
@@ -132,6 +138,39 @@ int main() {
   try {
     auto t = algorithms::spmv::merge_path_flat(csr, x, y);
     check("algorithms::spmv::merge_path_flat", y, ref);
+    {
+      // the reference signature keeps its plan on the container: the second call re-uses it
+      // (no allocation), a forced tiling switches later calls to the band-tiled kernel, and
+      // values_changed() after an in-place write keeps the result in step with the live arrays
+      const auto* e1 = csr.plans().find(LOOPSB_SCHED_MERGE_PATH_FLAT);
+      const loopsb_plan_t* p1 = e1 ? e1->plan : nullptr;
+      thrust::fill(y.begin(), y.end(), -1.0f);
+      algorithms::spmv::merge_path_flat(csr, x, y);
+      const auto* e2 = csr.plans().find(LOOPSB_SCHED_MERGE_PATH_FLAT);
+      bool ok = p1 && e2 && e2->plan == p1 && e2->calls == 2 && !e2->tiled && csr.plans().size() == 1;
+      csr.plans().tiling = 1;
+      thrust::fill(y.begin(), y.end(), -1.0f);
+      algorithms::spmv::merge_path_flat(csr, x, y);
+      loopsb_tiled_info_t ti;
+      ok = ok && e2->plan == p1 && e2->tiled && loopsb_plan_tiled_info(e2->plan, &ti) == LOOPSB_OK && ti.grid_blocks > 0;
+      if (!ok) { std::printf("FAIL cached plan state (reuse / forced tiling)\n"); ++failures; }
+      check("algorithms::spmv::merge_path_flat (cached plan, band-tiled kernel)", y, ref);
+      // in-place update of the values: 2*A
+      thrust::transform(csr.values.begin(), csr.values.end(), csr.values.begin(), twice_fn());
+      csr.values_changed();
+      std::vector<float> ref2(ref);
+      for (auto& v : ref2) v *= 2.0f;
+      thrust::fill(y.begin(), y.end(), -1.0f);
+      algorithms::spmv::merge_path_flat(csr, x, y);      // re-tiles (tiling = 1) from the live values
+      check("algorithms::spmv::merge_path_flat after values_changed()", y, ref2);
+      thrust::transform(csr.values.begin(), csr.values.end(), csr.values.begin(), halve_fn());
+      csr.values_changed();
+      csr.plans().tiling = 0;
+      thrust::fill(y.begin(), y.end(), -1.0f);
+      algorithms::spmv::merge_path_flat(csr, x, y);
+      check("algorithms::spmv::merge_path_flat (tiling off again)", y, ref);
+      csr.plans().tiling = -1;
+    }
     // the re-usable plan with the band-tiled copy (forced: this matrix is below the cost model's size)
     algorithms::spmv::merge_path_plan_t plan(csr, 0, true, true);
     for (int rep = 0; rep < 3; ++rep) {

@@ -124,3 +124,6 @@ def test_packed_and_direct_paths_are_bit_identical(monkeypatch):
     for _ in range(3):                          # the work counter is re-armed every launch
         spmv.bcsr_thread_mapped(B, xb, yp)
     assert torch.equal(yp, yd * 0.5)
+    B.values.mul_(4.0)                          # in place WITHOUT repack=True: torch's version counter is watched
+    spmv.bcsr_thread_mapped(B, xb, yp)
+    assert torch.equal(yp, yd * 2.0)

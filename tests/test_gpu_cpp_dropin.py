@@ -20,4 +20,4 @@ def test_cpp_dropin_program():
     print(p.stdout, p.stderr)
     assert p.returncode == 0, p.stdout + p.stderr
     lines = [l for l in p.stdout.splitlines() if l.startswith(("OK", "FAIL"))]
-    assert len(lines) == 22 and all(l.startswith("OK") for l in lines), p.stdout
+    assert len(lines) == 25 and all(l.startswith("OK") for l in lines), p.stdout

@@ -56,7 +56,7 @@ def ragged_mtx(tmp_path_factory):
 def test_every_reference_unit_test_passes():
     _need_suite()
     bins = _binaries("unit.")
-    assert len(bins) >= 29, bins
+    assert len(bins) >= 26, bins      # one binary per unittests/test_*.cu
     summary = []
     for b in bins:
         p = subprocess.run([b], capture_output=True, text=True, timeout=600)

@@ -183,3 +183,52 @@ def test_dirty_steps_take_the_general_path(oracle, monkeypatch):
         y, info = _run(off, idx, val, x, 80, 640, geometry, repeat=2, want_info=True)
         assert info["flagged_steps"] > 0
         np.testing.assert_array_equal(y, oracle.spmv(off, idx, val, x))
+
+
+def test_in_place_value_updates_never_return_stale_results(oracle):
+    """The band-tiled copy holds VALUES and is keyed by array addresses. An in-place update
+    must not be answered from the old copy: the container watches torch's version counters
+    (loopsb_plan_invalidate), and ``values_changed()`` covers writes torch cannot see."""
+    from loops_b200 import _lib, csr_t
+    from loops_b200.algorithms import spmv
+    off, idx, val = random_csr(3000, 2500, 0.01, seed=21, exact=True, empty_every=7, heavy_row=(5, 2000))
+    x = oracle.x_recipe_int(2500)
+    A = csr_t(3000, 2500, off, idx, val)
+    xd = torch.as_tensor(x).cuda()
+    y = torch.full((3000,), float("nan"), device="cuda")
+    spmv.merge_path_flat(A, xd, y, tiled=True)
+    y1 = oracle.spmv(off, idx, val, x)
+    np.testing.assert_array_equal(y.cpu().numpy(), y1)
+    plan = A.plan(_lib.SCHED_MERGE_PATH_FLAT, tiled=True)
+    assert plan.tiled_info() is not None
+    # 1. torch-visible in-place write, default (auto) call: the copy is dropped, the plain kernel answers
+    A.values.mul_(2.0)
+    y.fill_(float("nan"))
+    spmv.merge_path_flat(A, xd, y)
+    np.testing.assert_array_equal(y.cpu().numpy(), 2.0 * y1)
+    assert A.plan(_lib.SCHED_MERGE_PATH_FLAT).tiled_info() is None
+    # 2. forced again: re-tiled from the live values
+    y.fill_(float("nan"))
+    spmv.merge_path_flat(A, xd, y, tiled=True)
+    np.testing.assert_array_equal(y.cpu().numpy(), 2.0 * y1)
+    assert A.plan(_lib.SCHED_MERGE_PATH_FLAT, tiled=True).tiled_info() is not None
+    # 3. forced call right after another in-place write: re-tiled, not stale
+    A.values.mul_(0.25)
+    y.fill_(float("nan"))
+    spmv.merge_path_flat(A, xd, y, tiled=True)
+    np.testing.assert_array_equal(y.cpu().numpy(), 0.5 * y1)
+    # 4. a write behind torch's back (``.data`` has its own version counter) + values_changed()
+    A.values.data.mul_(4.0)
+    A.values_changed()
+    y.fill_(float("nan"))
+    spmv.merge_path_flat(A, xd, y, tiled=True)
+    np.testing.assert_array_equal(y.cpu().numpy(), 2.0 * y1)
+    # 5. column ids changed in place as well (rotate every column id by one)
+    idx2 = ((idx.astype(np.int64) + 1) % 2500).astype(np.int32)
+    order = np.concatenate([off[r] + np.argsort(idx2[off[r]:off[r + 1]], kind="stable") for r in range(3000)]) \
+        if len(idx2) else np.zeros(0, np.int64)
+    A.indices.copy_(torch.as_tensor(idx2[order]).cuda())
+    A.values.copy_(torch.as_tensor(val[order]).cuda())
+    y.fill_(float("nan"))
+    spmv.merge_path_flat(A, xd, y, tiled=True)
+    np.testing.assert_array_equal(y.cpu().numpy(), oracle.spmv(off, idx2[order], val[order], x))
