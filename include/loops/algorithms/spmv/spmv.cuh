@@ -122,19 +122,24 @@ inline util::timer_t merge_path_flat(csr_t<int, int, float>& csr, vector_t<float
   auto& e = csr.plans().get(LOOPSB_SCHED_MERGE_PATH_FLAT, lay, detail::raw(csr.offsets), indices, values, csr.rows,
                             csr.cols, csr.nnzs, std::size_t(lay.pitch), stream);
   const int mode = csr.plans().tiling >= 0 ? csr.plans().tiling : detail::tiling_mode();
-  if (!e.tiled && mode != 0 && e.tile_after != -1 && csr.nnzs > 0) {
-    if (e.tile_after == -2) {
-      int64_t n = -1;
-      error::throw_if_status(loopsb_plan_tile_breakeven(e.plan, static_cast<int32_t>(csr.cols), &n),
-                             "loopsb_plan_tile_breakeven");
-      e.tile_after = mode == 1 ? 0 : static_cast<long long>(n);
+  const bool forced = mode == 1;
+  if (!e.tiled && mode != 0 && csr.nnzs > 0 && !(forced ? e.declined_forced : e.declined)) {
+    long long after = 0;
+    if (!forced) {
+      if (e.tile_after == -2) {
+        int64_t n = -1;
+        error::throw_if_status(loopsb_plan_tile_breakeven(e.plan, static_cast<int32_t>(csr.cols), &n),
+                               "loopsb_plan_tile_breakeven");
+        e.tile_after = static_cast<long long>(n);
+      }
+      after = e.tile_after;
     }
-    if (e.tile_after >= 0 && e.calls >= e.tile_after) {
+    if (after >= 0 && e.calls >= after) {
       const int rc = loopsb_plan_tile_csr(e.plan, indices, values, static_cast<int32_t>(csr.cols),
-                                          mode == 1 ? LOOPSB_TILE_FORCE : 0, stream);
+                                          forced ? LOOPSB_TILE_FORCE : 0, stream);
       if (rc != LOOPSB_OK && rc != LOOPSB_ERR_UNSUPPORTED) error::throw_if_status(rc, "loopsb_plan_tile_csr");
       e.tiled = rc == LOOPSB_OK;
-      if (!e.tiled) e.tile_after = -1;   // declined: do not ask again for these arrays
+      if (!e.tiled) (forced ? e.declined_forced : e.declined) = true;   // do not ask again for these arrays
     }
   }
   return detail::run(csr.plans(), lay, LOOPSB_SCHED_MERGE_PATH_FLAT, values, indices, nullptr,

@@ -63,6 +63,8 @@ class plan_cache_t {
     long long calls = 0;         ///< SpMV calls since the plan was made / last invalidated
     long long tile_after = -2;   ///< -2 not asked yet, -1 never, else calls after which a band-tiled copy pays
     bool tiled = false;          ///< the plan holds a band-tiled copy of the matrix (loopsb_plan_tile_csr)
+    bool declined = false;       ///< the library's cost model declined the copy for these arrays
+    bool declined_forced = false;  ///< ... even when forced (the format cannot hold this matrix)
   };
 
   /// merge_path_flat on CSR: -1 = follow LOOPSB_TILED (default: after the break-even number of

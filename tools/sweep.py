@@ -26,29 +26,37 @@ PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if 
     os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 
 
-def time_ms(fn, warm=5, reps=30):
+def time_ms(fn, warm=5, reps=5, batch=20):
+    """Median / best over `reps` batches of `batch` back-to-back launches, one CUDA event pair
+    per batch on the current stream (how bench.py times its step): launch latency is hidden
+    behind the previous launch, as in any real use, instead of being added to every sample."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record(); b.synchronize()
-        ts.append(a.elapsed_time(b))
+        a.record()
+        for _ in range(batch):
+            fn()
+        b.record(); b.synchronize()
+        ts.append(a.elapsed_time(b) / batch)
     ts.sort()
     return ts[len(ts) // 2], ts[0]
 
 
-def main():
-    small = "--small" in sys.argv
+def run(small=False, reference=True, log=sys.stderr):
+    """All of BASELINE configs[2] and configs[3] on the current device; returns the result document.
+    `reference=False` leaves out the reference's own kernels (bench.py's `extra` block: product code only)."""
     rows = cols = (1 << 16) if small else (1 << 20)
     nnz = rows * 32
-    out = {"rows": rows, "nnz": nnz, "peak_gbs": PEAK, "cells": [], "reference_gpu": [], "bcsr": None}
+    out = {"rows": rows, "nnz": nnz, "peak_gbs": PEAK, "cells": [], "reference_gpu": [], "bcsr": None,
+           "timing": "median of 5 batches of 20 back-to-back launches, one CUDA event pair per batch"}
     off, idx, val = g.synth_csr(rows, cols, nnz, device="cuda")
     A = csr_t.from_tensors(rows, cols, off, idx, val)
     x = g.x_recipe(cols, device="cuda")
     y0 = torch.empty(rows, device="cuda")
-    spmv.merge_path_flat(A, x, y0)
+    spmv.merge_path_flat(A, x, y0, tiled=False)
     bytes_csr = nnz * 8 + (rows + 1) * 4 + cols * 4 + rows * 4
     bytes_coo = nnz * 12 + cols * 4 + rows * 4
 
@@ -61,11 +69,17 @@ def main():
                              "gnnz_per_s": nnz / med / 1e6, "algorithmic_gb_per_s": nbytes / med / 1e6,
                              "roofline_frac": nbytes / med / 1e6 / PEAK, "bit_equal_to_merge_csr": ok})
         print(f"{layout:4s} {sched:16s} {med*1e3:9.1f} us  {nnz/med/1e6:7.1f} Gnnz/s  {nbytes/med/1e6:7.0f} GB/s  ok={ok}",
-              file=sys.stderr)
+              file=log)
 
     scheds = ("merge_path_flat", "work_oriented", "group_mapped", "thread_mapped")
     for name in scheds:
-        cell("csr", name, spmv.CELLS[("csr", name)], A, bytes_csr)
+        fn = spmv.CELLS[("csr", name)]
+        if name == "merge_path_flat":     # the kernel that reads the CSR arrays; the plan-owned tiled copy is its own line
+            fn = lambda c, xx, yy, sync=True: spmv.merge_path_flat(c, xx, yy, sync=sync, tiled=False)
+        cell("csr", name, fn, A, bytes_csr)
+    cell("csr", "merge_path_flat+band_tiled_plan",
+         lambda c, xx, yy, sync=True: spmv.merge_path_flat(c, xx, yy, sync=sync, tiled="auto"), A, bytes_csr)
+    spmv.merge_path_flat(A, x, y0, tiled=False)   # drop the tiled copy again (290 MB)
     coo = csr_to_coo_device(A)
     for name in scheds:
         cell("coo", name, spmv.CELLS[("coo", name)], coo, bytes_coo)
@@ -79,7 +93,7 @@ def main():
 
     # ---- reference kernels on the same GPU (context: the kernels to beat) ----
     so = os.path.join(ROOT, "oracle", "_ref", "libloopsref_gpu.so")
-    if os.path.exists(so):
+    if reference and os.path.exists(so):
         G = C.CDLL(so)
         P = lambda a: a.ctypes.data_as(C.c_void_p)
         ho, hi, hv, hx = off.cpu().numpy(), idx.cpu().numpy(), val.cpu().numpy(), x.cpu().numpy()
@@ -92,7 +106,7 @@ def main():
             t = inner.value if inner.value > 0 else ms.value
             out["reference_gpu"].append({"kernel": nm, "rc": rc, "ms_best_wrapper": ms.value, "ms_best_timer_t": inner.value,
                                          "gnnz_per_s": nnz / t / 1e6, "y_equal": bool(np.array_equal(yr, y0h))})
-            print(f"reference {nm:18s} {t*1e3:9.1f} us  {nnz/t/1e6:7.1f} Gnnz/s  y_equal={np.array_equal(yr, y0h)}", file=sys.stderr)
+            print(f"reference {nm:18s} {t*1e3:9.1f} us  {nnz/t/1e6:7.1f} Gnnz/s  y_equal={np.array_equal(yr, y0h)}", file=log)
 
     # ---- config 4: BCSR 4x4 bf16 on tcgen05 ----
     nbr = (1 << 12) if small else (1 << 18)
@@ -115,8 +129,12 @@ def main():
     out["bcsr"] = {"block_rows": nbr, "blocks": nb, "ms_median": med, "ms_min": best, "blocks_per_s": nb / med * 1e3,
                    "algorithmic_bytes": nbytes, "algorithmic_gb_per_s": nbytes / med / 1e6,
                    "roofline_frac": nbytes / med / 1e6 / PEAK, "exact_vs_float64": ok}
-    print(f"bcsr4x4 bf16 tcgen05: {med*1e3:.1f} us  {nbytes/med/1e6:.0f} GB/s  frac {nbytes/med/1e6/PEAK:.3f}  ok={ok}", file=sys.stderr)
-    print(json.dumps(out))
+    print(f"bcsr4x4 bf16 tcgen05: {med*1e3:.1f} us  {nbytes/med/1e6:.0f} GB/s  frac {nbytes/med/1e6/PEAK:.3f}  ok={ok}", file=log)
+    return out
+
+
+def main():
+    print(json.dumps(run(small="--small" in sys.argv)))
 
 
 if __name__ == "__main__":
