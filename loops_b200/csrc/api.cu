@@ -333,11 +333,87 @@ int launch_tiled(bt::plan_data* d, const float* x, float* y, cudaStream_t s) {
     p.l2_guard = guard;
   }
   bt::kernel_fn k = bt::kernel_for(d->g.warps, d->g.es, d->prof != nullptr);
+  // Launches after the first on a copy use PROGRAMMATIC DEPENDENT LAUNCH instead of a cooperative launch:
+  // the CTAs of launch n+1 take the SMs the CTAs of launch n leave and run their prologue (barrier set-up,
+  // first matrix-stream requests, y tile) while the rest of launch n is still reducing; nothing launch n
+  // reads or writes is touched before griddepcontrol.wait (measured on config 2: 61.1 -> 57.9 us per SpMV
+  // back to back). The first launch after a (re)build stays fully ordered behind the builder kernels.
+  // Without the cooperative launch's co-residency guarantee the q CTAs of a row block still wait for each
+  // other, which is safe as long as no OTHER chain of these grids can be partially resident at the same time
+  // (two such grids could hold each other's SMs). On one stream launch n+1 only starts once every CTA of
+  // launch n has started, so a single stream is always safe; the rule for several streams: an event is
+  // recorded after every band-tiled launch, and a launch is PDL only when every earlier launch made on a
+  // DIFFERENT stream of this device is known to have completed; otherwise it is cooperative, which cannot
+  // start until all of its CTAs fit. LOOPSB_TILED_PDL=0 turns PDL off (e.g. processes sharing the GPU via MPS).
+  static const int pdl_env = getenv("LOOPSB_TILED_PDL") ? atoi(getenv("LOOPSB_TILED_PDL")) : 1;
+  struct launch_tracker {
+    cudaStream_t cur = nullptr;         // stream of the latest band-tiled launch
+    cudaEvent_t cur_ev = nullptr;       // recorded after it
+    std::vector<cudaEvent_t> foreign;   // last events of the streams used before `cur`, while still pending
+    std::vector<cudaEvent_t> spare;
+    bool broken = false;                // an event could not be created or recorded: stay cooperative
+  };
+  static std::mutex pdl_mu;
+  static launch_tracker trackers[64];
+  int dev = 0;
+  LOOPSB_CUDA_TRY(cudaGetDevice(&dev));
+  const bool track = pdl_env == 1 && dev >= 0 && dev < 64;   // (2 = PDL without the tracking events: measurement only)
+  p.pdl = 0;
+  bool coop_ok = true;
+  if (track) {
+    std::lock_guard<std::mutex> lock(pdl_mu);
+    launch_tracker& T = trackers[dev];
+    if (T.cur_ev && T.cur != s) {          // stream switch: the old stream's tail becomes a foreign event
+      T.foreign.push_back(T.cur_ev);
+      T.cur_ev = nullptr;
+    }
+    for (size_t f = 0; f < T.foreign.size();) {
+      const cudaError_t qe = cudaEventQuery(T.foreign[f]);
+      if (qe == cudaSuccess) {
+        T.spare.push_back(T.foreign[f]);
+        T.foreign[f] = T.foreign.back();
+        T.foreign.pop_back();
+      } else {
+        (void)cudaGetLastError();
+        ++f;
+      }
+    }
+    coop_ok = T.foreign.empty() && !T.broken;
+  }
+  if (pdl_env != 0 && d->peers && d->launched && !d->prof && (pdl_env == 2 || (track && coop_ok))) p.pdl = 1;
+  auto note_launch = [&]() {
+    if (!track) return;
+    std::lock_guard<std::mutex> lock(pdl_mu);
+    launch_tracker& T = trackers[dev];
+    if (!T.cur_ev) {
+      if (!T.spare.empty()) { T.cur_ev = T.spare.back(); T.spare.pop_back(); }
+      else if (cudaEventCreateWithFlags(&T.cur_ev, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); T.cur_ev = nullptr; }
+    }
+    T.cur = s;
+    if (!T.cur_ev || cudaEventRecord(T.cur_ev, s) != cudaSuccess) { (void)cudaGetLastError(); T.broken = true; }
+  };
+  if (p.pdl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(d->g.grid());
+    cfg.blockDim = dim3(d->g.cta_threads());
+    cfg.dynamicSmemBytes = size_t(d->smem);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    LOOPSB_CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p));
+    note_launch();
+    return LOOPSB_OK;
+  }
+  d->launched = true;
   if (d->peers) {
     // every CTA resident at once (checked at plan time): the CTAs of a row block may wait for each other
     void* args[] = {&p};
     LOOPSB_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(k), dim3(d->g.grid()),
                                                 dim3(d->g.cta_threads()), args, size_t(d->smem), s));
+    note_launch();
   } else {
     k<<<d->g.grid(), d->g.cta_threads(), d->smem, s>>>(p);
     LOOPSB_CUDA_TRY(cudaGetLastError());
@@ -435,6 +511,8 @@ int loopsb_tiled_image_build_host(int32_t num_rows, int32_t num_cols, const int3
   g.nb = geometry[0]; g.q = geometry[1]; g.warps = geometry[2];
   g.cb = geometry[3]; g.xb = geometry[4]; g.es = geometry[5];
   if (const char* e = getenv("LOOPSB_TILED_PACK")) g.pack = atoi(e) != 0;
+  if (const char* e = getenv("LOOPSB_TILED_ROUND")) g.quantum = atoi(e) != 0 ? g.es : 1;
+  if (const char* e = getenv("LOOPSB_TILED_SPLIT")) g.midpoint = atoi(e) != 0;
   int rc = LOOPSB_OK;
   try {
     rc = bt::build_host(img->im, g, num_rows, num_cols, host_offsets, host_indices, host_values);

@@ -76,6 +76,9 @@ struct geom {
   // chosen
   int nb = 0, q = 0, warps = 0, cb = 0, xb = 0, es = 0;
   int pack = 1;   // bank-aware placement of the entries inside a step (LOOPSB_TILED_PACK=0 turns it off)
+  int midpoint = 1; // consumer-warp row ranges are cut at row midpoints (0 = round-1 rule: at row starts; LOOPSB_TILED_SPLIT=0)
+  int quantum = 1;  // a stream's step count is rounded up to a multiple of this (1 = none; LOOPSB_TILED_ROUND=1 restores
+                    // the round-1 format, whole prefetch groups of `es` steps: +1.2 % traffic, slowest warp of a CTA +1.7 %)
   // derived
   int rb = 0, rw = 0, cq = 0, nband = 0;
   int rows = 0, cols = 0;
@@ -207,10 +210,15 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
         int w = 0;
         wb[0] = 0;
         for (int r = b0; r < b1; ++r) {
-          // row r opens warp w+1 once the rows before it hold w+1 shares of the nonzeros
-          while (w + 1 < g.warps && acc * g.warps >= tot * (w + 1) && tot > 0) wb[++w] = r - b0;
+          // row r belongs to the warp whose share of the nonzeros holds the row's MIDPOINT:
+          // w(r) = min(warps-1, floor((2 acc + v) warps / (2 tot))). Rows are atomic (no two warps
+          // share a y row), so a boundary is off by at most half a row -- with rows of up to 256
+          // entries per part that is one step of a ~74-step stream instead of two.
+          const long long v = rowpart[size_t(r) * g.q + qi];
+          const long long mid = g.midpoint ? v : 0;
+          while (w + 1 < g.warps && (2 * acc + mid) * g.warps >= 2 * tot * (w + 1) && tot > 0) wb[++w] = r - b0;
           wmap[size_t(r) * g.q + qi] = uint8_t(w);
-          acc += rowpart[size_t(r) * g.q + qi];
+          acc += v;
         }
         while (w + 1 <= g.warps) wb[++w] = b1 - b0;
         for (int k = 0; k < g.warps; ++k) rw_of_block[rbi] = std::max(rw_of_block[rbi], wb[k + 1] - wb[k]);
@@ -257,7 +265,7 @@ inline int build_host(host_image& im, geom g, int rows, int cols, const int* off
         end[b] = e;
       }
       long long nsteps = (pos + kStep - 1) / kStep;
-      nsteps = (nsteps + g.es - 1) / g.es * g.es;   // whole prefetch groups (all-padding steps at the end)
+      nsteps = (nsteps + g.quantum - 1) / g.quantum * g.quantum;   // g.quantum = es: whole prefetch groups (all-padding steps at the end)
       if (nsteps > 65535) { too_long.store(nsteps); nsteps = 0; }
       // band tables: empty bands borrow the first step of the next non-empty one
       int next_fs = int(nsteps);
@@ -535,7 +543,10 @@ struct params {
   int rows, cols, rb, cq, cb, xb, es, nband, q, nb;
   int l2_ahead;         // steps between the L2 prefetch and the register prefetch
   int l2_guard;         // 1: the L2 prefetch stops at the end of the warp's own stream
-  int peers;            // 1: cooperative launch, the q CTAs of a row block share the reduction
+  int peers;            // 1: every CTA resident at once, the q CTAs of a row block share the reduction
+  int pdl;              // 1: launched with programmatic stream serialization (see launch_tiled): everything that
+                        //    does not depend on the previous kernel of the stream -- barrier set-up, the first
+                        //    matrix-stream requests, the zeroed y tile -- runs before griddepcontrol.wait
   long long* prof;      // PROFILE builds: 8 counters per consumer warp, then 4 wall-clock stamps per CTA
 };
 
@@ -676,12 +687,13 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
       loops::tma::barrier_arrive(&xfull[k]);
     }
   };
+  if (p.pdl) asm volatile("griddepcontrol.launch_dependents;");   // the next kernel of the stream may start filling freed SMs
   if (boss) {
     for (int k = 0; k < p.xb; ++k) {
       loops::tma::barrier_init(&xfull[k], 1);
       loops::tma::barrier_init(&xempty[k], WARPS);
     }
-    for (int b = 0; b < min(p.xb, p.nband); ++b) request_band(b, b);
+    if (!p.pdl) for (int b = 0; b < min(p.xb, p.nband); ++b) request_band(b, b);
   }
   const bool consumer = warp < WARPS;
   const int ws = consumer ? cta * WARPS + warp : 0;
@@ -700,6 +712,13 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
   }
   for (int i = tid; i < ys_words; i += (WARPS + 1) * 32) ys[i] = 0.f;
   if (tid < 4) xs[p.xb * p.cb + tid] = 0.f;
+  if (p.pdl && boss) {
+    // x (and y, the partial rows, the counters) belong to the previous kernel of the stream until it
+    // has completed: the producer thread waits for that here, every other thread is ordered behind
+    // it by the barrier below and by the x ring (no consumer passes its first band before this).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int b = 0; b < min(p.xb, p.nband); ++b) request_band(b, b);
+  }
   __syncthreads();
   if (PROFILE && stamps && boss) stamps[1] = wall_ns();
 
@@ -762,11 +781,13 @@ __global__ void __launch_bounds__((WARPS + 1) * 32, 1) spmv_bt_kernel(const para
     // (Issuing the x gathers of step s+1 ahead of the y updates of step s was
     // tried and measured slower: a warp that then blocks on the x ring sits on
     // y updates it could have retired. Steps are processed one at a time.)
-    // nsteps is a multiple of DEPTH (the plan pads streams with all-padding steps)
-    // and DEPTH spare steps follow the last stream, so prefetches need no guard.
+    // DEPTH spare steps follow the last stream, so prefetches need no guard. A stream's
+    // step count need not be a multiple of DEPTH: the last group stops at the stream's
+    // end (warp-uniform test); what its unused registers hold is the head of the next stream.
     for (int s0 = 0; s0 < nsteps; s0 += DEPTH) {
 #pragma unroll
       for (int k = 0; k < DEPTH; ++k) {
+        if (s0 + k >= nsteps) break;
         // (the step is used in place and its registers are re-loaded only when the
         // step is done: copying them out first made ptxas rotate registers with
         // moves that wait on the load just issued -- a synchronous "prefetch")
@@ -976,6 +997,7 @@ struct plan_data {
   long long bytes = 0;
   int smem = 0;
   int peers = 0;   // the grid fits the device in one wave: launch cooperatively, share the q-way reduction
+  bool launched = false;   // a first launch on this copy has been enqueued (launch_tiled: later ones may use PDL)
   long long* prof = nullptr;  // LOOPSB_DEBUG_PHASES: 8 counters per consumer warp
 };
 
@@ -1028,6 +1050,8 @@ inline geom choose_geom(int rows, int cols, int sms, int max_smem) {
   if (over[4] > 0) g.xb = over[4];
   if (over[5] > 0) g.es = over[5];
   if (const char* e = getenv("LOOPSB_TILED_PACK")) g.pack = atoi(e) != 0;
+  if (const char* e = getenv("LOOPSB_TILED_ROUND")) g.quantum = atoi(e) != 0 ? g.es : 1;
+  if (const char* e = getenv("LOOPSB_TILED_SPLIT")) g.midpoint = atoi(e) != 0;
   if (over[0] > 0) {
     g.nb = over[0];
   } else {

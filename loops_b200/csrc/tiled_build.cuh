@@ -28,7 +28,7 @@ namespace dev {
 
 // ---- geometry constants handed to the kernels ----
 struct gconst {
-  int rows, cols, q, warps, cb, xb, es, cq, nband, nb, rb, ns;
+  int rows, cols, q, warps, cb, xb, es, cq, nband, nb, rb, ns, quantum, midpoint;
 };
 
 __global__ void rowpart_kernel(const int* __restrict__ off, const int* __restrict__ idx, int rows, int cols, int q,
@@ -45,8 +45,8 @@ __global__ void rowpart_kernel(const int* __restrict__ off, const int* __restric
 }
 
 // Block per (row block, part): warp that owns every row of the block inside this
-// part -- w(r) = min(warps-1, floor(acc_before(r) * warps / tot)), the closed form
-// of the host's "open the next warp once the rows before hold their share" loop.
+// part -- w(r) = min(warps-1, floor((2 acc_before(r) + v(r)) * warps / (2 tot))), the closed
+// form of the host's "the warp whose share holds the row's midpoint" loop.
 __global__ void __launch_bounds__(256)
     warp_map_kernel(const int* __restrict__ rowpart, const int* __restrict__ blk_begin, gconst g,
                     unsigned char* __restrict__ wmap) {
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256)
     if (r < b1) {
       int w = 0;
       if (tot > 0) {
-        const long long k = before * g.warps / tot;
+        const long long k = (2 * before + (g.midpoint ? v : 0)) * g.warps / (2 * tot);   // the row's midpoint (host loop's closed form)
         w = int(k < g.warps - 1 ? k : g.warps - 1);
       }
       wmap[(long long)r * g.q + qi] = (unsigned char)w;
@@ -140,7 +140,7 @@ __global__ void layout_kernel(const int* __restrict__ count, gconst g, int* __re
     pos = e;
   }
   long long nsteps = (pos + kStep - 1) / kStep;
-  nsteps = (nsteps + g.es - 1) / g.es * g.es;
+  nsteps = (nsteps + g.quantum - 1) / g.quantum * g.quantum;
   if (nsteps > 65535) { atomicMax(too_long, 1); nsteps = 0; }
   int next_fs = int(nsteps);
   for (int b = g.nband - 1; b >= 0; --b) {
@@ -428,7 +428,7 @@ inline int build_device(plan_data* d, geom g, int rows, int cols, const int* d_o
   for (int k = 0; k < g.nb; ++k) rb_max = std::max(rb_max, blk_begin[k + 1] - blk_begin[k]);
   g.rb = rb_max;
   g.rw = 0;   // (rows per warp is only reported by the host builder)
-  dev::gconst gc{rows, cols, g.q, g.warps, g.cb, g.xb, g.es, g.cq, g.nband, g.nb, g.rb, ns};
+  dev::gconst gc{rows, cols, g.q, g.warps, g.cb, g.xb, g.es, g.cq, g.nband, g.nb, g.rb, ns, g.quantum, g.midpoint};
 
   // ---- temporaries ----
   int *rowpart = nullptr, *count = nullptr, *start = nullptr, *keyfirst = nullptr, *steps_of = nullptr, *flags = nullptr;

@@ -1,8 +1,11 @@
 """GPU parity: every SpMV entry point, through the C ABI, against the oracle.
 
 Bars: bit-exact y where the arithmetic is exactly representable or sequential
-(integer x with k/8 values; thread_mapped on any input); otherwise relative
-error <= 1e-6 against the f64-accumulating reference (north_star tolerance) --
+(integer x with k/8 values; thread_mapped on any input); otherwise
+|y - y64| <= 1e-6 * L1(row) against the f64-accumulating reference, AND
+element-wise |y - y64| <= 1e-6 * |y64| on every row whose |y64| is at least half
+its L1 mass (north_star tolerance; rows dominated by cancellation have no
+meaningful element-wise relative error in fp32) --
 plus the reference's own acceptance rules (count_errors == 0 and a Wilkinson
 verdict of NOT_A_BUG, util/reference.hxx:116-131,278-337)."""
 import numpy as np
@@ -36,6 +39,13 @@ def _assert_close(oracle, off, idx, val, x, y, label):
     rel = np.abs(y.astype(np.float64) - y64) / l1
     assert np.all(np.isfinite(y)), label
     assert rel.max() <= REL_TOL, (label, float(rel.max()))
+    # element-wise |y - y64| <= 1e-6 |y64| wherever the row is not dominated by cancellation
+    # (|y64| >= half its L1 mass); rows below that bar are held to the L1-scaled bound only,
+    # which is what fp32 summation error is proportional to ("Tolerance")
+    well = np.abs(y64) >= 0.5 * l1
+    if well.any():
+        elem = np.abs(y.astype(np.float64) - y64)[well] / np.abs(y64[well])
+        assert elem.max() <= REL_TOL, (label, "element-wise", float(elem.max()))
     assert oracle.count_errors(y, oracle.spmv(off, idx, val, x)) == 0, label
     rep = oracle.rigorous(off, idx, val, x, y)
     assert rep.gpu_overruns == 0, (label, "POTENTIAL_BUG")

@@ -232,3 +232,57 @@ def test_in_place_value_updates_never_return_stale_results(oracle):
     y.fill_(float("nan"))
     spmv.merge_path_flat(A, xd, y, tiled=True)
     np.testing.assert_array_equal(y.cpu().numpy(), oracle.spmv(off, idx2[order], val[order], x))
+
+
+def test_two_plans_on_two_streams_interleaved(oracle):
+    """Launches after the first on a plan use programmatic dependent launch instead of a cooperative
+    launch -- only while no band-tiled launch of ANOTHER stream can still be running (two partially
+    resident grids could hold each other's SMs); otherwise they fall back to the cooperative launch.
+    Two plans driven from two streams without any synchronisation in between must neither hang nor
+    disturb each other's results."""
+    from loops_b200 import csr_t
+    from loops_b200.algorithms import spmv
+    mats = []
+    for seed in (31, 32):
+        off, idx, val = random_csr(6000, 5000, 0.004, seed=seed, exact=True, empty_every=11, heavy_row=(7, 3000))
+        x = oracle.x_recipe_int(5000)
+        A = csr_t(6000, 5000, off, idx, val)
+        mats.append((A, torch.as_tensor(x).cuda(), oracle.spmv(off, idx, val, x)))
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    ys = [[torch.full((6000,), float("nan"), device="cuda") for _ in range(8)] for _ in range(2)]
+    torch.cuda.synchronize()
+    for rep in range(8):
+        for k in (0, 1):
+            A, xd, _ = mats[k]
+            with torch.cuda.stream(streams[k]):
+                spmv.merge_path_flat(A, xd, ys[k][rep], stream=streams[k], sync=False, tiled=True)
+    torch.cuda.synchronize()
+    for k in (0, 1):
+        for rep in range(8):
+            np.testing.assert_array_equal(ys[k][rep].cpu().numpy(), mats[k][2])
+    # and back on one stream: a chain of dependent launches (x of launch n+1 is y of launch n)
+    A, xd, ref = mats[0]
+    sq = csr_t(*_square_power_matrix())
+    v = torch.ones(sq.rows, device="cuda")
+    w = torch.empty_like(v)
+    want = np.ones(sq.rows, np.float32)
+    o, i_, vv = sq.host()
+    for _ in range(6):
+        spmv.merge_path_flat(sq, v, w, sync=False, tiled=True)
+        v, w = w, v
+        want = oracle.spmv(o, i_, vv, want)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(v.cpu().numpy(), want)
+
+
+def _square_power_matrix():
+    """3000 x 3000, entries 1/2 or 1/4 on a few bands: repeated products stay exactly representable."""
+    n = 3000
+    off = np.zeros(n + 1, np.int32)
+    idx, val = [], []
+    for r in range(n):
+        cols = sorted({r, (r * 7 + 3) % n, (r + 1) % n, (r * 13 + 11) % n})
+        idx += cols
+        val += [0.25 if (c + r) % 2 else 0.5 for c in cols]
+        off[r + 1] = len(idx)
+    return n, n, off, np.asarray(idx, np.int32), np.asarray(val, np.float32)

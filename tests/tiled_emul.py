@@ -71,7 +71,7 @@ def emulate(img, x, rows, cols):
             resident = [-1] * xb     # band sitting in each ring slot (as this warp sees it)
             held = []                # bands acquired and not yet released, oldest first
             done = set()             # bands released
-            assert (end - base) % es == 0, "streams are whole prefetch groups"
+            # (round-1 format: whole prefetch groups, (end - base) % es == 0; the kernel no longer needs it)
 
             def acquire(keep):
                 nonlocal acq
