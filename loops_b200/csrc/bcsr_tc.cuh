@@ -67,7 +67,10 @@ struct plan_data {
   long long* item_tile = nullptr;   // [num_items] first tile of the item
   long long total_tiles = 0;
   const void* packed_key = nullptr; // the values pointer the copy was made from
-  int* work_counter = nullptr;      // next work item to hand out (packed kernel: dynamic, longest first)
+  int* work_counter = nullptr;      // two counters handing out work items (packed kernel: dynamic, longest first); launch n
+                                    // uses counter n & 1 and re-arms the other one for launch n + 1 (no memset per launch)
+  int launch_parity = 0;
+  bool packed_launched = false;     // a first launch on the current packed copy has been enqueued (later ones may use PDL)
 };
 
 __global__ void row_lengths_kernel(const int* __restrict__ off, int n,
@@ -458,8 +461,15 @@ __global__ void __launch_bounds__(kThreads)
     spmv_bcsr4x4_bf16_packed_kernel(const uint16_t* __restrict__ packed, const long long* __restrict__ item_tile,
                                     const uint16_t* __restrict__ x, float* __restrict__ y,
                                     const int4* __restrict__ items, int num_items, float* __restrict__ partial,
-                                    int num_rows, const int4* __restrict__ item_rows, int* __restrict__ work_counter) {
+                                    int num_rows, const int4* __restrict__ item_rows, int* __restrict__ counters,
+                                    int parity, int pdl) {
   __shared__ tc_shared_packed sm;
+  int* const work_counter = counters + parity;
+  // pdl: launched with programmatic stream serialization -- TMEM, barriers and the first A tiles of the
+  // CTA's first item (plan-owned constants) are set up while the previous kernel of the stream drains;
+  // x, y, the partial rows and the work counters are only touched after griddepcontrol.wait.
+  if (pdl) asm volatile("griddepcontrol.launch_dependents;");
+  bool ordered = false;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int b = tid >> 2;      // block-row slot inside the group
@@ -522,6 +532,11 @@ __global__ void __launch_bounds__(kThreads)
       }
     }
 
+    if (!ordered) {
+      if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+      if (blockIdx.x == 0 && tid == 0) counters[parity ^ 1] = 0;   // the previous launch (its last user) is complete
+      ordered = true;
+    }
     // the first tiles of this CTA's NEXT item go to L2 now, so that its start pays an L2
     // hit instead of an HBM round trip (one bulk prefetch per tile, issued by one thread)
     if (tid == 32) {
@@ -640,6 +655,7 @@ inline int pack(plan_data* p, const uint16_t* values, const int* block_cols, cud
                                                           p->packed);
   LOOPSB_CUDA_TRY(cudaGetLastError());
   p->packed_key = values;
+  p->packed_launched = false;   // the next launch must be fully ordered behind the pack kernel
   return LOOPSB_OK;
 }
 
@@ -648,6 +664,7 @@ __global__ void __launch_bounds__(128)
     bcsr_split_reduce_kernel(const int4* __restrict__ split, const float* __restrict__ partial,
                              const int* __restrict__ order, int num_block_rows, int num_rows,
                              float* __restrict__ y) {
+  asm volatile("griddepcontrol.launch_dependents;");   // a PDL-launched SpMV behind this kernel may start its set-up
   const int4 s = __ldg(split + blockIdx.x);
   const int m = threadIdx.x;
   float acc = 0.0f;
@@ -688,11 +705,31 @@ inline int run(plan_data* p, const loopsb_layout_t* lay, const uint16_t* values,
                            cudaSharedmemCarveoutMaxShared);
       carved = true;
     }
-    if (!p->work_counter) LOOPSB_CUDA_TRY(cudaMalloc(&p->work_counter, 4));
-    LOOPSB_CUDA_TRY(cudaMemsetAsync(p->work_counter, 0, 4, stream));
-    spmv_bcsr4x4_bf16_packed_kernel<<<grid, kThreads, 0, stream>>>(p->packed, p->item_tile, x, y, p->items,
-                                                                 p->num_items, p->partial, num_rows, p->item_rows,
-                                                                 p->work_counter);
+    if (!p->work_counter) {
+      LOOPSB_CUDA_TRY(cudaMalloc(&p->work_counter, 8));
+      LOOPSB_CUDA_TRY(cudaMemsetAsync(p->work_counter, 0, 8, stream));   // once; afterwards launch n re-arms n + 1's counter
+      p->launch_parity = 0;
+    }
+    // LOOPSB_BCSR_PDL (default 1): launches after the first on a packed copy are programmatic dependent
+    // launches (see the kernel); a kernel of another kind in front of it simply never triggers early.
+    static const bool pdl_env = !getenv("LOOPSB_BCSR_PDL") || atoi(getenv("LOOPSB_BCSR_PDL")) != 0;
+    const int pdl = pdl_env && p->packed_launched ? 1 : 0;
+    const int parity = p->launch_parity;
+    p->launch_parity ^= 1;
+    p->packed_launched = true;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    LOOPSB_CUDA_TRY(cudaLaunchKernelEx(&cfg, spmv_bcsr4x4_bf16_packed_kernel, (const uint16_t*)p->packed,
+                                       (const long long*)p->item_tile, x, y, (const int4*)p->items, p->num_items,
+                                       p->partial, num_rows, (const int4*)p->item_rows, p->work_counter, parity, pdl));
   } else
     spmv_bcsr4x4_bf16_kernel<<<grid, kThreads, 0, stream>>>(lay->offsets, block_cols, values, x, y, p->order,
                                                           p->num_block_rows, p->items, p->num_items, p->partial,

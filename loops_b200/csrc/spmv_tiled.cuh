@@ -58,7 +58,7 @@ constexpr int kPerLane = 4;
 constexpr int kStep = kLanes * kPerLane;  // entries per step
 constexpr int kStepWords = 2 * kStep;     // 256 words = 1 KB
 constexpr uint32_t kFlagBit = 0x80000000u;
-constexpr int kL2Ahead = 6;               // steps between the L2 prefetch and the register prefetch
+constexpr int kL2Ahead = 2;               // steps between the L2 prefetch and the register prefetch (swept 2..12 on B200 with PDL launches: 2 is best warm and cold, profiles/tiled_l2ahead_r02.txt)
 // Step control word (ballot of bit 31 of the slot-0 ids):
 //   bit 0       dirty: some row of the step is NOT one contiguous range of cells (general path)
 //   bit 29      long : every row is contiguous, but some run covers three or more lanes
