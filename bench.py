@@ -391,8 +391,12 @@ def main():
         # The step IS one launch of this kernel, so the timed region (one event pair around
         # K back-to-back launches) divided by K is its average duration, launch gaps included.
         # An event pair around every single launch adds ~2 us of record/start latency to a
-        # 60 us kernel; it is kept below as kernel_ms_event_pair_*.
-        k_ms, k_src = ms_step, "timed region / K (step = 1 launch of this kernel; CUDA events on the launching stream)"
+        # 60 us kernel and keeps consecutive launches from overlapping; it is kept below as
+        # kernel_ms_event_pair_*.
+        k_ms, k_src = ms_step, ("timed region / K (step = 1 launch of this kernel; CUDA events on the launching stream). "
+                                "Launches after the first are programmatic dependent launches: the prologue of launch n+1 "
+                                "runs under the write-out of launch n, so this average period is shorter than one launch "
+                                "timed alone (kernel_ms_event_pair_*, the serialised ncu list); LOOPSB_TILED_PDL=0 turns it off")
     else:
         k_ms, k_src = k_pair_ms, "mean of per-launch CUDA event pairs on the launching stream (second pass)"
     achieved = local_bytes / (k_ms * 1e-3) / 1e9
