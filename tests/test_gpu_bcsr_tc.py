@@ -127,3 +127,35 @@ def test_packed_and_direct_paths_are_bit_identical(monkeypatch):
     B.values.mul_(4.0)                          # in place WITHOUT repack=True: torch's version counter is watched
     spmv.bcsr_thread_mapped(B, xb, yp)
     assert torch.equal(yp, yd * 2.0)
+
+
+def test_full_size_config4_exact():
+    """BASELINE configs[3] at FULL size -- 262,144 block-rows / 8,388,608 4x4 bf16 blocks (the workload
+    tools/bcsr_bench.py and bench.py's `extra` time): y equal bit for bit to a float64 evaluation with
+    torch ops (values k/8, x integers 1..10: every product and sum is exact), on the first launch (fully
+    ordered) and after several back-to-back launches (programmatic dependent launches, alternating work
+    counters)."""
+    from loops_b200 import generate as g
+    from loops_b200.algorithms import spmv
+    from loops_b200.container import bcsr_t
+    nbr = 1 << 18
+    nb = nbr * 32
+    b_off, b_col, _ = g.synth_csr(nbr, nbr, nb, device="cuda")
+    e = torch.arange(nb * 16, device="cuda", dtype=torch.int64)
+    b_val = (((g._lsr(g.mix64(e ^ 0x5151), 33) % 16) + 1).to(torch.float32) / 8.0).to(torch.bfloat16)
+    del e
+    B = bcsr_t.from_tensors(4, 4, nbr * 4, nbr * 4, nb * 16, b_off, b_col, b_val)
+    xb = g.x_recipe(nbr * 4, device="cuda").to(torch.bfloat16)
+    yb = torch.full((nbr * 4,), float("nan"), device="cuda")
+    spmv.bcsr_thread_mapped(B, xb, yb)
+    rowb = torch.repeat_interleave(torch.arange(nbr, device="cuda"), (b_off[1:] - b_off[:-1]).long(), output_size=nb)
+    xs = xb.double()[(b_col.long()[:, None] * 4 + torch.arange(4, device="cuda")[None, :])]      # [nb, 4]
+    prod = (b_val.double().view(nb, 4, 4) * xs[:, None, :]).sum(2)                                  # [nb, 4]
+    ref = torch.zeros(nbr, 4, dtype=torch.float64, device="cuda").index_add_(0, rowb, prod).view(-1)
+    del xs, prod, rowb
+    assert torch.equal(yb.double(), ref)
+    for _ in range(5):
+        yb.fill_(float("nan"))
+        spmv.bcsr_thread_mapped(B, xb, yb, sync=False)
+    torch.cuda.synchronize()
+    assert torch.equal(yb.double(), ref)
