@@ -360,8 +360,11 @@ int launch_tiled(bt::plan_data* d, const float* x, float* y, cudaStream_t s) {
   const bool track = pdl_env == 1 && dev >= 0 && dev < 64;   // (2 = PDL without the tracking events: measurement only)
   p.pdl = 0;
   bool coop_ok = true;
+  // decision, launch and event record are one critical section: two host threads launching on two
+  // streams of the same device must not both see "nothing foreign in flight"
+  std::unique_lock<std::mutex> pdl_lock(pdl_mu, std::defer_lock);
   if (track) {
-    std::lock_guard<std::mutex> lock(pdl_mu);
+    pdl_lock.lock();
     launch_tracker& T = trackers[dev];
     if (T.cur_ev && T.cur != s) {          // stream switch: the old stream's tail becomes a foreign event
       T.foreign.push_back(T.cur_ev);
@@ -381,9 +384,8 @@ int launch_tiled(bt::plan_data* d, const float* x, float* y, cudaStream_t s) {
     coop_ok = T.foreign.empty() && !T.broken;
   }
   if (pdl_env != 0 && d->peers && d->launched && !d->prof && (pdl_env == 2 || (track && coop_ok))) p.pdl = 1;
-  auto note_launch = [&]() {
+  auto note_launch = [&]() {   // (pdl_lock is held)
     if (!track) return;
-    std::lock_guard<std::mutex> lock(pdl_mu);
     launch_tracker& T = trackers[dev];
     if (!T.cur_ev) {
       if (!T.spare.empty()) { T.cur_ev = T.spare.back(); T.spare.pop_back(); }
