@@ -681,6 +681,7 @@ def main():
                                                                "roofline_frac", "bit_equal_to_merge_csr")}
                                            for c in doc["cells"]],
                          "config4_bcsr4x4_bf16_tcgen05": doc["bcsr"], "ell_pitch": doc.get("ell_pitch"),
+                         "spmm_csr_n32": doc.get("spmm"),
                          "timing": doc["timing"],
                          "note": "same box, after the headline; every cell checked bit-equal to merge_path_flat/CSR "
                                  "before it is timed; roofline_frac = the layout's algorithmic bytes / time / measured HBM peak"}

@@ -130,6 +130,35 @@ def run(small=False, reference=True, log=sys.stderr):
                    "algorithmic_bytes": nbytes, "algorithmic_gb_per_s": nbytes / med / 1e6,
                    "roofline_frac": nbytes / med / 1e6 / PEAK, "exact_vs_float64": ok}
     print(f"bcsr4x4 bf16 tcgen05: {med*1e3:.1f} us  {nbytes/med/1e6:.0f} GB/s  frac {nbytes/med/1e6/PEAK:.3f}  ok={ok}", file=log)
+    del B, xb, yb, ref
+    torch.cuda.empty_cache()
+
+    # ---- SpMM (reference algorithms/spmm/thread_mapped.cuh:28-53): C = A B on the config-2 matrix,
+    # B and C dense row-major with n = 32 columns. Last, and guarded: it is a SIMT kernel that carries no
+    # roofline claim -- the figure is here so that it is on record, not because it is tuned. ----
+    try:
+        from loops_b200.algorithms import spmm
+        n = 32
+        col = torch.arange(cols * n, device="cuda", dtype=torch.int64)
+        Bd = ((g._lsr(g.mix64(col ^ 0x7171), 33) % 10) + 1).to(torch.float32).view(cols, n)      # integers 1..10: exact sums
+        del col
+        Cd = torch.full((rows, n), float("nan"), device="cuda")
+        spmm.thread_mapped(A, Bd, Cd)
+        # independent check, one dense column at a time through the SpMV path (merge_path_flat/CSR)
+        ok = True
+        yk = torch.empty(rows, device="cuda")
+        for k in (0, n // 2, n - 1):
+            spmv.merge_path_flat(A, Bd[:, k].contiguous(), yk, tiled=False)
+            ok = ok and bool(torch.equal(yk, Cd[:, k]))
+        med, best = time_ms(lambda: spmm.thread_mapped(A, Bd, Cd, sync=False), warm=2, reps=3, batch=5)
+        nbytes = nnz * 8 + (rows + 1) * 4 + cols * n * 4 + rows * n * 4
+        out["spmm"] = {"n": n, "ms_median": med, "ms_min": best, "gflop_per_s": 2.0 * nnz * n / med / 1e6,
+                       "algorithmic_bytes": nbytes, "algorithmic_gb_per_s": nbytes / med / 1e6,
+                       "roofline_frac": nbytes / med / 1e6 / PEAK, "columns_equal_to_spmv": ok,
+                       "kernel": "sk::spmm_csr_row_warp (SIMT, warp per row x 32 columns; not tuned)"}
+        print(f"spmm n={n}: {med*1e3:.1f} us  {nbytes/med/1e6:.0f} GB/s  frac {nbytes/med/1e6/PEAK:.3f}  ok={ok}", file=log)
+    except Exception as e:          # never lose the cells above to this one
+        out["spmm"] = {"error": repr(e)[:200]}
     return out
 
 
