@@ -151,3 +151,58 @@ def test_unpacked_steps_can_be_dirty(lib, oracle, monkeypatch):
     x = oracle.x_recipe_int(64)
     img = _check(lib, oracle, 20, 64, off, idx, val, x, (1, 1, 1, 8, 2, 2))
     assert img["g"]["flagged_entries"] > 0 and img["g"]["flagged_steps"] > 0
+
+
+@pytest.mark.parametrize("env", [{}, {"LOOPSB_TILED_ROUND": "1"}, {"LOOPSB_TILED_SPLIT": "0"},
+                                 {"LOOPSB_TILED_ROUND": "1", "LOOPSB_TILED_SPLIT": "0"}])
+def test_random_matrices_and_geometries_under_every_builder_variant(lib, oracle, monkeypatch, env):
+    """Seeded random shapes, densities, heavy rows and geometries, through the round-2 builder (streams end at
+    their last real step; warp boundaries at row midpoints) and the round-1 rules it can be switched back to:
+    every image must satisfy all format invariants of the emulation and reproduce the oracle's y bit for bit."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(2024)
+    done = 0
+    for trial in range(40):
+        rows, cols = int(rng.integers(1, 400)), int(rng.integers(1, 700))
+        dens = float(rng.choice([0.005, 0.02, 0.1, 0.4]))
+        heavy = (int(rng.integers(0, rows)), int(rng.integers(1, cols + 1))) if rng.random() < 0.5 else None
+        off, idx, val = random_csr(rows, cols, dens, seed=1000 + trial, empty_every=int(rng.choice([0, 3, 7])),
+                                   heavy_row=heavy, exact=True)
+        if off[-1] == 0:
+            continue
+        cb = int(rng.choice([4, 8, 16, 64, 256]))
+        geometry = (int(rng.integers(1, 7)), int(rng.integers(1, 5)), int(rng.choice([1, 2, 4, 8, 12, 16])), cb,
+                    int(rng.integers(2, 5)), int(rng.integers(2, 5)))
+        x = oracle.x_recipe_int(cols)
+        rc, img = build_image(lib, rows, cols, off, idx, val, geometry)
+        if rc == 3:        # the control word cannot hold this many starting bands per step: reported, not built
+            continue
+        assert rc == 0, (geometry, lib.loopsb_last_error())
+        y, _ = emulate(img, x, rows, cols)
+        np.testing.assert_array_equal(y, oracle.spmv(off, idx, val, x), err_msg=str((trial, rows, cols, geometry)))
+        nst = np.diff(img["stream_base"])
+        if env.get("LOOPSB_TILED_ROUND") == "1":
+            assert np.all(nst % geometry[5] == 0)          # round-1 format: whole prefetch groups
+        done += 1
+    assert done >= 25
+
+
+def test_midpoint_split_balances_the_warps_of_the_bench_workload(lib, monkeypatch):
+    """Round-2 rule: a row goes to the warp whose share of the nonzeros holds its midpoint. On a 2^17-row cut of
+    the bench generator with the production proportions (24 warps, ~1100 rows per warp, rows of up to 1024
+    entries, 7168-column bands) the slowest warp of a CTA -- what its finishing time follows -- gets shorter
+    and the spread of stream lengths shrinks, against the round-1 rule (boundary at the row's start)."""
+    from loops_b200 import generate as g
+    rows = cols = 1 << 17
+    off, idx, val = g.synth_csr(rows, cols, rows * 32)
+    off, idx, val = off.numpy(), idx.numpy(), val.numpy()
+    geometry = (5, 4, 24, 7168, 3, 3)
+    stats = {}
+    for split in ("0", "1"):
+        monkeypatch.setenv("LOOPSB_TILED_SPLIT", split)
+        rc, img = build_image(lib, rows, cols, off, idx, val, geometry)
+        assert rc == 0
+        nst = np.diff(img["stream_base"]).reshape(-1, geometry[2])
+        stats[split] = (float(nst.max(1).mean()), int(nst.max() - nst.min()))
+    assert stats["1"][0] < stats["0"][0] and stats["1"][1] < stats["0"][1], stats
