@@ -1,5 +1,5 @@
 #!/bin/bash
-# L2-resident head of the band-tiled plan's matrix copy: parity with the keep-loads on, then a sweep of its size
+# (historic) L2-resident head of the band-tiled plan's matrix copy: the LOOPSB_TILED_PIN_MB experiment of round 2 -- measured (profiles/tiled_ab_r02.txt), dropped, and the env knob no longer exists in the library
 mkdir -p gpurun_out
 LOOPSB_TILED_PIN_MB=64 timeout 300 python -m pytest tests/test_gpu_tiled.py tests/test_gpu_tiled_build.py -x -q > gpurun_out/pytest_tiled.log 2>&1; echo "pytest(pin on) rc=$?"; tail -3 gpurun_out/pytest_tiled.log
 for MB in ${PIN_LIST:-0 24 40 56 72 96 0}; do

@@ -1,4 +1,5 @@
 #!/bin/bash
+# finer LOOPSB_TILED_L2AHEAD sweep of the band-tiled kernel (profiles/tiled_l2ahead_r02.txt)
 mkdir -p gpurun_out
 for A in 6 2 3 4 6 3; do
   LOOPSB_TILED_L2AHEAD=$A timeout 120 python bench.py --gpus 1 --steps 20 --warmup 5 --no-extra --no-cpu-baseline > gpurun_out/bench_ahead$A.json 2> gpurun_out/bench_ahead$A.err
